@@ -1,0 +1,107 @@
+"""Deterministic synthetic "radio" workloads.
+
+Used by bench.py, the parity tests and oracle/make_golden.py so that all three
+see the same inputs.  Generation is numpy ``RandomState`` (a frozen stream, so
+the same seed gives the same samples on every box) and is not part of the
+timed region anywhere.
+
+A stream is a band-limited noise bed (white N(0, 0.1^2) through a one-pole
+low-pass) with pattern clips planted at seeded offsets; some offsets are forced
+to straddle chunk boundaries.  Patterns are a mix of noise-like "jingles",
+chirps (some shorter than the 0.5 s short-clip threshold) and marker-tone sines
+declared the way an ``.apd.toml`` ``source = "sine"`` clip is
+(reference pattern_config.py:106-108: float32 phase).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Optional
+
+import numpy as np
+
+
+def _one_pole(x: np.ndarray, a: float) -> np.ndarray:
+    from scipy.signal import lfilter
+    return lfilter([1.0 - a], [1.0, -a], x).astype(np.float32)
+
+
+def make_patterns(n: int, sr: int = 8000, seed: int = 1, min_s: float = 0.3, max_s: float = 10.0,
+                  tone_every: int = 8, chirp_every: int = 8) -> list[dict[str, Any]]:
+    """n patterns with lengths linspace(min_s, max_s, n) seconds."""
+    rs = np.random.RandomState(seed)
+    out: list[dict[str, Any]] = []
+    lengths = np.linspace(min_s, max_s, n) if n > 1 else np.array([min_s])
+    for i, sec in enumerate(lengths):
+        ns = int(round(float(sec) * sr))
+        kind = "jingle"
+        if tone_every and i % tone_every == tone_every - 1:
+            kind = "tone"
+        elif chirp_every and i % chirp_every == 0:
+            kind = "chirp"
+        if kind == "tone":
+            f0 = float(rs.uniform(900.0, 1200.0))
+            t = np.arange(ns, dtype=np.float32) / np.float32(sr)
+            audio = (0.9 * np.sin(2 * np.pi * f0 * t)).astype(np.float32)
+            out.append({"name": f"p{i:03d}_tone", "audio": audio, "strategy": "marker_tone",
+                        "strategy_params": {"dominant_frequency_hz": f0}})
+        elif kind == "chirp":
+            f_a, f_b = float(rs.uniform(300, 900)), float(rs.uniform(1500, 3200))
+            t = np.arange(ns, dtype=np.float64) / sr
+            ph = 2 * np.pi * (f_a * t + (f_b - f_a) * t * t / (2 * max(float(sec), 1e-9)))
+            audio = (0.8 * np.sin(ph) * np.hanning(ns)).astype(np.float32)
+            out.append({"name": f"p{i:03d}_chirp", "audio": audio, "strategy": None, "strategy_params": {}})
+        else:
+            w = rs.standard_normal(ns).astype(np.float32)
+            w = _one_pole(w, float(rs.uniform(0.2, 0.8)))
+            env = 0.6 + 0.4 * np.sin(2 * np.pi * rs.uniform(0.5, 3.0) * np.arange(ns) / sr + rs.uniform(0, 6.28))
+            audio = (0.3 * w / (np.std(w) + 1e-12) * env).astype(np.float32)
+            out.append({"name": f"p{i:03d}_jingle", "audio": audio, "strategy": None, "strategy_params": {}})
+    return out
+
+
+def make_stream(seconds: float, patterns: list[dict[str, Any]], sr: int = 8000, seed: int = 0,
+                plants_per_pattern: int = 2, chunk_seconds: Optional[int] = 60,
+                bed_sigma: float = 0.1, gains: tuple[float, ...] = (1.0, 0.5)
+                ) -> tuple[np.ndarray, list[tuple[str, int, float]]]:
+    """Returns (float32 stream, [(pattern name, start sample, gain)])."""
+    rs = np.random.RandomState(seed)
+    n = int(round(seconds * sr))
+    bed = rs.standard_normal(n).astype(np.float32) * np.float32(bed_sigma)
+    audio = _one_pole(bed, 0.5)
+    plants: list[tuple[str, int, float]] = []
+    occupied: list[tuple[int, int]] = []
+    C = int(chunk_seconds * sr) if chunk_seconds else 0
+    for pi, p in enumerate(patterns):
+        L = p["audio"].size
+        if L + 2 >= n:
+            continue
+        for k in range(plants_per_pattern):
+            for _attempt in range(50):
+                if C and k == 0 and n > C + L and (pi % 2 == 0):
+                    # straddle a chunk boundary: start inside the last L samples of a chunk
+                    b = int(rs.randint(1, max(2, n // C))) * C
+                    start = b - int(rs.randint(1, L))
+                else:
+                    start = int(rs.randint(0, n - L - 1))
+                if start < 0 or start + L >= n:
+                    continue
+                if any(start < e + L and s - L < start + L for s, e in occupied):
+                    continue
+                break
+            else:
+                continue
+            g = float(gains[(pi + k) % len(gains)])
+            duck = 0.02 if p.get("strategy") == "marker_tone" else 0.1
+            pad = L if p.get("strategy") == "marker_tone" else 0   # quiet flanks for tone clips
+            a0, a1 = max(0, start - pad), min(n, start + L + pad)
+            audio[a0:a1] *= np.float32(duck)
+            audio[start:start + L] += np.float32(g) * p["audio"]
+            occupied.append((a0, a1))
+            plants.append((p["name"], start, g))
+    return audio.astype(np.float32), plants
+
+
+def describe(patterns: list[dict[str, Any]], sr: int) -> dict[str, Any]:
+    ls = [p["audio"].size for p in patterns]
+    return {"n_patterns": len(patterns), "min_len": min(ls), "max_len": max(ls),
+            "sliding_windows": sorted({math.ceil(l / sr) for l in ls})}
