@@ -1,0 +1,385 @@
+"""B200-native ``AudioPatternDetector`` -- drop-in for the reference class of the same name.
+
+Same constructor / ``find_clip_in_audio`` / ``get_config`` surface, exceptions and
+result layout as the reference (audio_pattern_detector/audio_pattern_detector.py:84-371),
+but the per-chunk work -- loudness normalisation, FFT cross-correlation against every
+clip, peak picking and the Step-2 verifiers -- runs as batched CUDA kernels behind the
+C ABI in include/apd_b200.h.  The host keeps only what the reference also does in
+Python: argument validation, the chunk read loop, timestamp arithmetic in the
+reference's exact order of float operations (:439-456, :585) and the per-chunk
+ordering of callbacks (:324-327).
+
+There is no CPU fallback: constructing a detector needs a CUDA device and the built
+``libapd_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import os
+import sys
+from collections.abc import Callable
+from dataclasses import dataclass
+from typing import Any, Optional, TypedDict
+
+import numpy as np
+from numpy.typing import NDArray
+
+from . import _lib
+from .audio_clip import AudioClip, AudioStream
+from .audio_utils import DEFAULT_TARGET_SAMPLE_RATE
+from .detection_utils import get_pure_tone_frequency
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_SECONDS_PER_CHUNK = 60            # reference :33
+SHORT_CLIP_DURATION_THRESHOLD = 0.5       # reference :36
+MARKER_TONE_STRATEGY = "marker_tone"      # reference :38
+DEFAULT_BATCH_CHUNKS = 16
+
+PatternDetectedCallback = Callable[[str, float], None]
+
+
+class ClipConfig(TypedDict):
+    duration_seconds: float
+    sliding_window_seconds: int
+
+
+class DetectorConfig(TypedDict):
+    default_seconds_per_chunk: int
+    min_chunk_size_seconds: int
+    sample_rate: int
+    clips: dict[str, ClipConfig]
+
+
+@dataclass
+class Candidate:
+    """One verified or rejected peak, with the scores the verifier computed (device results)."""
+    chunk: int
+    clip: str
+    peak: int
+    kind: str                 # "normal" | "short" | "tone"
+    accept: bool
+    skipped: bool
+    height: float
+    similarity_whole: float
+    similarity_middle: float
+    pearson: tuple[float, float, float]
+    tone: tuple[tuple[float, ...], ...]
+    timestamp: float
+
+
+@dataclass
+class ScanResult:
+    peak_times: dict[str, list[float]]
+    events: list[tuple[float, str]]           # callback order
+    candidates: list[Candidate]
+    unit_trace: Optional[dict[tuple[int, str], dict[str, Any]]]
+    total_time: float
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("audio_pattern_detector_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+class AudioPatternDetector:
+
+    def __init__(self, audio_clips: list[AudioClip], debug_mode: bool = False,
+                 seconds_per_chunk: int | None = DEFAULT_SECONDS_PER_CHUNK,
+                 target_sample_rate: int | None = None, debug_dir: str = "./tmp",
+                 height_min: float | None = None, *, device: int | None = None,
+                 max_batch_chunks: int | None = None) -> None:
+        self.audio_clips = audio_clips
+        self.debug_mode = debug_mode
+        self.debug_dir = debug_dir
+        self.height_min = height_min
+        self.normalize = True
+        self.target_sample_rate = target_sample_rate if target_sample_rate is not None else DEFAULT_TARGET_SAMPLE_RATE
+        sr = self.target_sample_rate
+
+        seen: set[str] = set()
+        longest = 0
+        for clip in audio_clips:                                           # reference :105-115
+            if clip.name in seen:
+                raise ValueError(f"clip {clip.name} needs to be unique")
+            if clip.sample_rate != sr:
+                raise ValueError(f"clip {clip.name} needs to be {sr} sample rate")
+            seen.add(clip.name)
+            longest = max(longest, len(clip.audio))
+
+        if seconds_per_chunk is None or seconds_per_chunk < 1:             # reference :117-120
+            seconds_per_chunk = math.ceil(longest / sr) * 2
+            logger.warning("seconds_per_chunk is not set or less than 1, setting it to longest clip * 2 seconds, "
+                           f"which is {seconds_per_chunk} seconds")
+        self._min_chunk_size = 0
+        for clip in audio_clips:                                           # reference :122-137
+            secs = len(clip.audio) / sr
+            sw = math.ceil(secs)
+            self._min_chunk_size = max(self._min_chunk_size, sw * 2)
+            if seconds_per_chunk < sw * 2:
+                raise ValueError(f"seconds_per_chunk {seconds_per_chunk} is too small for clip '{clip.name}' "
+                                 f"(duration: {secs:.2f}s, sliding_window: {sw}s, minimum chunk size: {sw * 2}s)")
+        self.seconds_per_chunk = seconds_per_chunk
+        if seconds_per_chunk != 60:                                        # reference :141-143
+            logger.warning(f"seconds_per_chunk {seconds_per_chunk} is not 60 seconds, turning off debug mode "
+                           "because it was made for 60 seconds only")
+            self.debug_mode = False
+
+        self._clip_strategies: dict[str, str | None] = {}
+        self._clip_strategy_params: dict[str, dict[str, Any]] = {}
+        self._tone_frequencies: dict[str, float] = {}
+        self._clip_lengths = [len(c.audio) for c in audio_clips]
+        self._sliding_windows = [math.ceil(n / sr) for n in self._clip_lengths]
+        self._chunk_samples = int(seconds_per_chunk * sr)
+        self._chunk_size = self._chunk_samples * 4                         # reference :224
+
+        for clip, sw in zip(audio_clips, self._sliding_windows):
+            secs = len(clip.audio) / sr
+            if sw != secs:                                                 # reference :162-163
+                print(f"adjusted sliding_window from {secs} to {sw} for {clip.name}", file=sys.stderr)
+
+        # ---- hand the clips to the device (pattern-side precompute happens in apd_create)
+        torch = _torch()
+        self._device = torch.cuda.current_device() if device is None else int(device)
+        self._max_batch = int(max_batch_chunks or os.environ.get("APD_B200_BATCH_CHUNKS", DEFAULT_BATCH_CHUNKS))
+        descs = (_lib.ClipDesc * len(audio_clips))()
+        self._keepalive: list[NDArray[np.float32]] = []
+        nan = float("nan")
+        for d, clip in zip(descs, audio_clips):
+            a = np.ascontiguousarray(clip.audio, dtype=np.float32)
+            self._keepalive.append(a)
+            d.samples = a.ctypes.data_as(C.POINTER(C.c_float))
+            d.length = a.size
+            d.strategy = _lib.STRATEGY_NORMAL
+            d.tone_hz = 0.0
+            for k in ("minimum_band_purity", "minimum_active_frame_ratio", "minimum_longest_active_run",
+                      "minimum_active_frame_mean_purity", "maximum_min_flank_purity", "maximum_max_flank_purity"):
+                setattr(d, k, nan)
+            self._clip_strategies[clip.name] = clip.strategy
+            self._clip_strategy_params[clip.name] = dict(clip.strategy_params)
+            if clip.strategy == MARKER_TONE_STRATEGY:                      # reference :214-221
+                d.strategy = _lib.STRATEGY_MARKER_TONE
+                freq = clip.strategy_params.get("dominant_frequency_hz")
+                if freq is None:
+                    freq = self._fallback_tone_frequency(a)
+                if freq is not None:
+                    self._tone_frequencies[clip.name] = float(freq)
+                    d.tone_hz = float(freq)
+                ver = clip.strategy_params.get("verification", {})
+                if isinstance(ver, dict):                                  # reference :694-705
+                    for k, v in ver.items():
+                        if hasattr(d, k):
+                            setattr(d, k, float(int(v)) if k == "minimum_longest_active_run" else float(v))
+        ctx = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.apd_create(C.byref(ctx), self._device, sr, self._chunk_samples,
+                                float(height_min) if height_min is not None else 0.0,
+                                len(audio_clips), descs, self._max_batch), "apd_create")
+        self._ctx = ctx
+        self._max_halo = max(self._sliding_windows, default=0) * sr
+        self._dev_buf = None
+        self._pinned = None
+
+    # ------------------------------------------------------------------ helpers
+    def _fallback_tone_frequency(self, raw: NDArray[np.float32]) -> Optional[float]:
+        """Reference :217-219 derives the frequency from the *normalised* clip; a pure gain
+        (plus clipping at +-1) does not move the dominant bin, so the raw clip is used."""
+        return get_pure_tone_frequency(raw, self.target_sample_rate)
+
+    def __del__(self) -> None:
+        ctx = getattr(self, "_ctx", None)
+        if ctx:
+            try:
+                _lib.lib().apd_destroy(ctx)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self._ctx = None
+
+    def close(self) -> None:
+        self.__del__()
+
+    def get_config(self) -> DetectorConfig:
+        """reference :226-246."""
+        clips: dict[str, ClipConfig] = {}
+        for clip, sw in zip(self.audio_clips, self._sliding_windows):
+            clips[clip.name] = {"duration_seconds": round(len(clip.audio) / self.target_sample_rate, 6),
+                                "sliding_window_seconds": sw}
+        return {"default_seconds_per_chunk": DEFAULT_SECONDS_PER_CHUNK, "min_chunk_size_seconds": self._min_chunk_size,
+                "sample_rate": self.target_sample_rate, "clips": clips}
+
+    def clip_info(self, index: int) -> dict[str, Any]:
+        """Pattern-side device results (loudness, self-correlation max, FFT size) for tests/inspection."""
+        sw, lufs, smax, nfft = C.c_int32(), C.c_double(), C.c_float(), C.c_int32()
+        _lib.check(_lib.lib().apd_clip_info(self._ctx, index, C.byref(sw), C.byref(lufs), C.byref(smax),
+                                            C.byref(nfft)), "apd_clip_info")
+        n = self._clip_lengths[index]
+        norm = np.empty(n, dtype=np.float32)
+        cc = np.empty(2 * n - 1, dtype=np.float32)
+        _lib.check(_lib.lib().apd_clip_normalized(self._ctx, index, norm.ctypes.data_as(C.POINTER(C.c_float))), "clip")
+        _lib.check(_lib.lib().apd_clip_self_correlation(self._ctx, index, cc.ctypes.data_as(C.POINTER(C.c_float))),
+                   "clip")
+        return {"sliding_window": sw.value, "lufs": lufs.value, "self_max": smax.value, "fft_points": nfft.value,
+                "normalized": norm, "self_correlation": cc}
+
+    # ------------------------------------------------------------------ timestamps
+    def _timestamp(self, peak: int, chunk: int, clip_index: int) -> float:
+        """reference :585 then :440-451, same order of float operations."""
+        sr = self.target_sample_rate
+        t = peak / sr
+        t = t - (self._sliding_windows[clip_index] if chunk > 0 else 0)
+        t = t + (chunk * self.seconds_per_chunk)
+        t = t - (self._clip_lengths[clip_index] / sr)
+        return t if t >= 0 else 0
+
+    # ------------------------------------------------------------------ device scan of one batch
+    def _scan_batch(self, dev_ptr: int, base_sample: int, n_samples: int, chunk_begin: int, chunk_end: int,
+                    want_trace: bool) -> tuple[list[Candidate], Optional[dict]]:
+        torch = _torch()
+        L = _lib.lib()
+        nb = chunk_end - chunk_begin
+        ncl = len(self.audio_clips)
+        cap = max(4096, nb * ncl * 4)
+        cands = (_lib.Candidate * cap)()
+        n = C.c_int32(0)
+        trace = (_lib.UnitTrace * (nb * ncl))() if want_trace else None
+        lufs = (C.c_double * (nb * ncl))() if want_trace else None
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.apd_scan(self._ctx, C.c_void_p(dev_ptr), base_sample, n_samples, chunk_begin, chunk_end,
+                              cands, cap, C.byref(n), trace, lufs, C.c_void_p(stream)), "apd_scan")
+        out: list[Candidate] = []
+        for i in range(n.value):
+            r = cands[i]
+            kind = _lib.KINDS[(r.flags >> _lib.KIND_SHIFT) & 3]
+            out.append(Candidate(chunk=r.chunk, clip=self.audio_clips[r.clip].name, peak=r.peak, kind=kind,
+                                 accept=bool(r.flags & _lib.FLAG_ACCEPT), skipped=bool(r.flags & _lib.FLAG_SKIPPED),
+                                 height=r.height, similarity_whole=r.similarity_whole,
+                                 similarity_middle=r.similarity_middle, pearson=tuple(r.pearson),
+                                 tone=tuple(tuple(seg) for seg in r.tone),
+                                 timestamp=self._timestamp(r.peak, r.chunk, r.clip)))
+            out[-1]._clip_index = r.clip  # type: ignore[attr-defined]
+        tr = None
+        if want_trace:
+            tr = {}
+            for ci in range(nb):
+                for p in range(ncl):
+                    u = trace[ci * ncl + p]
+                    tr[(chunk_begin + ci, self.audio_clips[p].name)] = {
+                        "absmax": u.absmax, "max_choose": u.max_choose, "n_out": u.n_out,
+                        "n_peaks": u.n_peaks, "lufs": lufs[ci * ncl + p]}
+        return out, tr
+
+    def _emit_batch(self, cands: list[Candidate], chunk_begin: int, chunk_end: int,
+                    peak_times: Optional[dict[str, list[float]]], events: list[tuple[float, str]],
+                    on_pattern_detected: Optional[PatternDetectedCallback]) -> None:
+        """Per chunk: clips in list order, then a stable sort by timestamp (reference :303-327)."""
+        by_chunk: dict[int, list[Candidate]] = {}
+        for c in cands:
+            if c.accept:
+                by_chunk.setdefault(c.chunk, []).append(c)
+        for i in range(chunk_begin, chunk_end):
+            hits = by_chunk.get(i, [])               # already ordered by (clip index, peak)
+            if peak_times is not None:
+                for c in hits:
+                    peak_times[c.clip].append(c.timestamp)
+            ordered = sorted(((c.timestamp, c.clip) for c in hits), key=lambda e: e[0])
+            for t, name in ordered:
+                events.append((t, name))
+                if on_pattern_detected:
+                    on_pattern_detected(name, t)
+
+    # ------------------------------------------------------------------ public scanning API
+    def scan_array(self, audio: "NDArray[np.float32] | Any", on_pattern_detected: Optional[PatternDetectedCallback] = None,
+                   collect_trace: bool = False) -> ScanResult:
+        """Scan a whole in-memory stream (numpy array or CUDA float32 tensor).
+
+        B200-side extension of the reference API: the stream is made device resident once and
+        scanned ``max_batch_chunks`` chunks per launch sequence."""
+        torch = _torch()
+        if isinstance(audio, np.ndarray):
+            dev = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(f"cuda:{self._device}")
+        else:
+            dev = audio.to(device=f"cuda:{self._device}", dtype=torch.float32).contiguous()
+        n = dev.numel()
+        C_ = self._chunk_samples
+        n_chunks = (n + C_ - 1) // C_
+        peak_times: dict[str, list[float]] = {c.name: [] for c in self.audio_clips}
+        events: list[tuple[float, str]] = []
+        all_cands: list[Candidate] = []
+        trace: Optional[dict] = {} if collect_trace else None
+        with torch.cuda.device(self._device):
+            for c0 in range(0, n_chunks, self._max_batch):
+                c1 = min(n_chunks, c0 + self._max_batch)
+                cands, tr = self._scan_batch(dev.data_ptr(), 0, n, c0, c1, collect_trace)
+                all_cands.extend(cands)
+                if trace is not None and tr:
+                    trace.update(tr)
+                self._emit_batch(cands, c0, c1, peak_times, events, on_pattern_detected)
+        total = 0.0
+        for i in range(n_chunks):                                           # reference :301
+            total += (min((i + 1) * C_, n) - i * C_) / self.target_sample_rate
+        return ScanResult(peak_times=peak_times, events=events, candidates=all_cands, unit_trace=trace,
+                          total_time=total)
+
+    def find_clip_in_audio(self, audio_stream: AudioStream,
+                           on_pattern_detected: PatternDetectedCallback | None = None,
+                           accumulate_results: bool = True) -> tuple[dict[str, list[float]] | None, float]:
+        """reference :248-371.  Reads ``seconds_per_chunk`` at a time like the reference, but hands
+        up to ``max_batch_chunks`` chunks to the device per scan; callbacks still arrive in the
+        reference's order (chunk by chunk, sorted by timestamp inside a chunk)."""
+        if audio_stream.sample_rate != self.target_sample_rate:
+            raise ValueError(f"full_streaming_audio_clip {audio_stream.name} needs to be "
+                             f"{self.target_sample_rate} sample rate")
+        torch = _torch()
+        sr = self.target_sample_rate
+        C_ = self._chunk_samples
+        peak_times: dict[str, list[float]] | None = (
+            {c.name: [] for c in self.audio_clips} if accumulate_results else None)
+        events: list[tuple[float, str]] = []
+        total_time = 0.0
+        src = audio_stream.audio_stream
+        halo = np.zeros(0, dtype=np.float32)          # tail of the previous batch (look-back)
+        chunk_index = 0
+        eof = False
+        cap = self._max_halo + self._max_batch * C_
+        with torch.cuda.device(self._device):
+            if self._dev_buf is None:
+                self._dev_buf = torch.empty(cap, dtype=torch.float32, device=f"cuda:{self._device}")
+                self._pinned = torch.empty(cap, dtype=torch.float32).pin_memory()
+            while not eof:
+                parts: list[NDArray[np.float32]] = []
+                while len(parts) < self._max_batch:
+                    data = src.read(self._chunk_size)
+                    if not data:
+                        eof = True
+                        break
+                    chunk = np.frombuffer(data, dtype="float32")
+                    total_time += len(chunk) / sr                           # reference :301
+                    parts.append(chunk)
+                    if len(chunk) != C_:
+                        # a short read is the stream's final chunk (reference :296-299 treats any
+                        # following read as a new chunk; fixed-size device chunks cannot)
+                        eof = True
+                        break
+                if not parts:
+                    break
+                for k, ch in enumerate(parts[:-1]):
+                    if len(ch) != C_:
+                        raise ValueError("audio stream returned a short chunk before the end of the stream")
+                new = np.concatenate(parts) if len(parts) > 1 else parts[0]
+                n_halo = halo.size
+                n_tot = n_halo + new.size
+                host = self._pinned[:n_tot].numpy()
+                host[:n_halo] = halo
+                host[n_halo:] = new
+                self._dev_buf[:n_tot].copy_(self._pinned[:n_tot], non_blocking=True)
+                c0, c1 = chunk_index, chunk_index + len(parts)
+                cands, _ = self._scan_batch(self._dev_buf.data_ptr(), c0 * C_ - n_halo, n_tot, c0, c1, False)
+                self._emit_batch(cands, c0, c1, peak_times, events, on_pattern_detected)
+                keep = min(self._max_halo, n_tot)
+                halo = host[n_tot - keep:n_tot].copy()
+                chunk_index = c1
+        return peak_times, total_time

@@ -1,0 +1,829 @@
+// C-ABI layer: context, pattern-side precompute and the batched scan pipeline.
+// See include/apd_b200.h for the contract and the reference interfaces each call replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/apd_b200.h"
+#include "internal.h"
+#include "loudness.h"
+#include "peaks.h"
+
+using namespace apd;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(APD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+namespace {
+
+struct ClipHost {
+    int L = 0, sw = 0, group = 0, strategy = 0, is_short = 0;
+    double tone_hz = 0.0, lufs = 0.0;
+    float self_max = 0.0f;
+    float* d_raw = nullptr;
+    float* d_norm = nullptr;
+    float* d_rev = nullptr;
+    float2* d_spec = nullptr;       // group-size spectrum of the reversed normalised clip
+    float* d_self_corr = nullptr;   // 2L-1
+    float* d_win_cache = nullptr;
+    int tone_P = 0;
+    double2* d_tone_chirp = nullptr;
+    double2* d_tone_tw = nullptr;
+};
+
+struct Group {
+    int sw = 0, halo = 0;
+    std::vector<int> clips;
+    Fft4Plan plan;
+    long long spec_off = 0;
+    int* d_clips = nullptr;
+    int2* d_sel = nullptr;
+    int max_L = 0;
+};
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n)
+{
+    return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+template <typename T>
+cudaError_t upload(T** p, const std::vector<T>& v)
+{
+    cudaError_t e = dalloc(p, v.size());
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+__global__ void k_prepare_clip(const float* __restrict__ raw, int L, const double* __restrict__ gain,
+                               float* __restrict__ norm, float* __restrict__ rev)
+{
+    const double g = *gain;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+        // reference lib.rs:220-227 (clip side keeps NaN; a silent clip is not a valid pattern)
+        double v = (double)raw[i] * g;
+        if (v == v) v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
+        const float f = (float)v;
+        norm[i] = f;
+        rev[L - 1 - i] = f;
+    }
+}
+
+// clip-side window-max down-sampling (reference lib.rs:283-318), one block per window
+__global__ void k_window_max(const float* __restrict__ cc, int lo, int hi, int ds, float* __restrict__ out)
+{
+    const int nw = hi - lo;
+    const double step = (double)nw / (double)ds;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ds; i += gridDim.x * blockDim.x) {
+        int a = (int)((double)i * step);
+        int b = (int)((double)(i + 1) * step);
+        if (b <= a) b = a + 1;
+        if (a >= nw) a = nw - 1;
+        if (b > nw) b = nw;
+        float m = -INFINITY;
+        for (int t = a; t < b; ++t) m = fmaxf(m, cc[lo + t]);
+        out[i] = m;
+    }
+}
+
+__global__ void k_select_group(const unsigned int* __restrict__ unit_max_bits, const float* __restrict__ self_max,
+                               const int* __restrict__ group_clips, int ng, int n_clips, int n_chunks, float height,
+                               int2* __restrict__ sel, int* __restrict__ sel_count)
+{
+    // ordered compaction by one CTA over the dense (ci, clip-in-group) units of one group
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int n_units = n_chunks * ng;
+    for (int u0 = 0; u0 < n_units; u0 += blockDim.x) {
+        const int u = u0 + threadIdx.x;
+        bool pass = false;
+        int ci = 0, clip = 0;
+        if (u < n_units) {
+            ci = u / ng;
+            clip = group_clips[u % ng];
+            const float am = __uint_as_float(unit_max_bits[(long long)ci * n_clips + clip]);
+            const float mc = fmaxf(self_max[clip], am);
+            pass = mc > 0.0f && (am / mc) >= height;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_tot[w] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; ++i) off += warp_tot[i];
+        if (pass) sel[off + __popc(bal & ((1u << lane) - 1))] = make_int2(ci, clip);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += warp_tot[i];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *sel_count = base;
+}
+
+__global__ void k_record_npeaks(const int2* __restrict__ sel, const int* __restrict__ sel_count, int slot0, int nslots,
+                                const int* __restrict__ n_peaks, int n_clips, int* __restrict__ unit_npeaks)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots || slot0 + s >= *sel_count) return;
+    const int2 u = sel[slot0 + s];
+    unit_npeaks[(long long)u.x * n_clips + u.y] = n_peaks[s];
+}
+
+}  // namespace
+
+struct apd_ctx {
+    int device = 0, sr = 0, n_clips = 0, maxB = 0;
+    long long C = 0;
+    float height = kDefaultHeight;
+    std::vector<ClipHost> clips;
+    std::vector<Group> groups;
+    KwConfig kw{};
+    std::map<int, Fft4Plan> self_plans;
+    long long launches = 0;
+
+    // per-clip device tables
+    int *d_clip_len = nullptr, *d_clip_group = nullptr, *d_strategy = nullptr, *d_is_short = nullptr;
+    int *d_win_lo = nullptr, *d_win_hi = nullptr, *d_win_ds = nullptr, *d_tone_P = nullptr;
+    float* d_self_max = nullptr;
+    const float** d_self_corr_ptrs = nullptr;
+    const float** d_win_cache_ptrs = nullptr;
+    const float2** d_clip_spec_ptrs = nullptr;
+    double *d_tone_hz = nullptr, *d_tone_thr = nullptr;
+    const double2** d_tone_chirp_ptrs = nullptr;
+    const double2** d_tone_tw_ptrs = nullptr;
+    SectionGeom* d_geoms = nullptr;
+    SectionGeom* h_geoms = nullptr;       // pinned
+
+    // workspace
+    int cells_stride = 0;
+    double *d_kw_state = nullptr, *d_kw_energy = nullptr, *d_kw_em1 = nullptr, *d_lufs = nullptr, *d_gain = nullptr;
+    long long spec_slab = 0;              // complex elements per chunk (sum of group M)
+    float2* d_spec = nullptr;
+    long long scratch_elems = 0;
+    float2* d_scratch = nullptr;
+    int inv_units = 0;                    // units per inverse launch
+    unsigned int* d_unit_max = nullptr;
+    int* d_unit_npeaks = nullptr;
+    int* d_counts = nullptr;              // [G] selected counts, [G] = out_count, [G+1] = overflow, [G+2] tone items
+    int* h_counts = nullptr;              // pinned mirror
+    int n_slots = 0;
+    long long corr_stride = 0, cand_stride = 0;
+    int peak_stride = 0;
+    float* d_corr = nullptr;
+    int* d_cand_idx = nullptr;
+    float* d_cand_val = nullptr;
+    unsigned char* d_cand_state = nullptr;
+    int* d_peaks = nullptr;
+    int *d_n_peaks = nullptr, *d_n_cands = nullptr;
+    apd_candidate* d_slot_cands = nullptr;
+    apd_candidate* d_out = nullptr;
+    int out_capacity = 0;
+    // tone
+    int tone_ctas = 0, tone_wl = 0, tone_item_cap = 0;
+    long long tone_stride = 0;
+    double2* d_tone_scratch = nullptr;
+    void* d_tone_items = nullptr;
+    double* d_tone_metrics = nullptr;
+
+    // state of the staged batch
+    const float* audio = nullptr;
+    long long base = 0, nsamp = 0;
+    int chunk_begin = 0, chunk_end = 0;
+    bool staged = false;
+};
+
+static void fill_geoms(apd_ctx* c)
+{
+    for (size_t g = 0; g < c->groups.size(); ++g) {
+        SectionGeom G;
+        G.audio = c->audio;
+        G.base = c->base;
+        G.total = c->base + c->nsamp;
+        G.chunk = c->C;
+        G.chunk0 = c->chunk_begin;
+        G.halo = c->groups[g].halo;
+        c->h_geoms[g] = G;
+    }
+}
+
+extern "C" const char* apd_last_error(void) { return g_err.c_str(); }
+
+static int self_correlation(apd_ctx* c, ClipHost& cl, unsigned int* d_tmp_max, int* d_tmp_int, float* d_zero_f,
+                            const float2** d_tmp_ptr)
+{
+    const int L = cl.L;
+    const int M_min = L < 16 ? 16 : L;                       // real length 2M >= 2L-1
+    std::string err;
+    auto it = c->self_plans.find(M_min);
+    if (it == c->self_plans.end()) {
+        Fft4Plan P;
+        if (!build_plan(M_min, &P, &err)) return fail(APD_ERR_UNSUPPORTED, err);
+        it = c->self_plans.emplace(M_min, P).first;
+    }
+    const Fft4Plan& P = it->second;
+    float2 *sa = nullptr, *sb = nullptr, *scr = nullptr;
+    CK(dalloc(&sa, (size_t)P.M));
+    CK(dalloc(&sb, (size_t)P.M));
+    CK(dalloc(&scr, (size_t)P.M));
+    SectionGeom Ga{cl.d_norm, 0, L, L, 0, 0}, Gb{cl.d_rev, 0, L, L, 0, 0};
+    launch_forward(P, Ga, nullptr, 0, 1, scr, sa, P.M, 0);
+    launch_forward(P, Gb, nullptr, 0, 1, scr, sb, P.M, 0);
+    CK(cudaMemset(d_tmp_max, 0, sizeof(unsigned int)));
+    const int Lh = L;
+    CK(cudaMemcpy(d_tmp_int + 1, &Lh, sizeof(int), cudaMemcpyHostToDevice));   // [0] = clip index 0, [1] = length
+    const float2* hp = sb;
+    CK(cudaMemcpy(d_tmp_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+    UnitSrc U{nullptr, d_tmp_int, 1, 0};
+    InvOut O{d_tmp_max, 1, cl.d_self_corr, (long long)(2 * L - 1), d_zero_f, d_tmp_int + 1};
+    launch_inverse_max(P, Ga, sa, P.M, U, 1, d_tmp_ptr, scr, O, 0);
+    launch_inverse_write(P, Ga, sa, P.M, U, 1, d_tmp_ptr, scr, O, 0);
+    CK(cudaDeviceSynchronize());
+    unsigned int bits = 0;
+    CK(cudaMemcpy(&bits, d_tmp_max, sizeof(bits), cudaMemcpyDeviceToHost));
+    memcpy(&cl.self_max, &bits, sizeof(float));
+    c->launches += 8;
+    cudaFree(sa);
+    cudaFree(sb);
+    cudaFree(scr);
+    return APD_OK;
+}
+
+extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t chunk_samples, float height_min,
+                          int n_clips, const apd_clip_desc* descs, int max_batch_chunks)
+{
+    if (!out || !descs || n_clips <= 0 || chunk_samples <= 0 || max_batch_chunks <= 0)
+        return fail(APD_ERR_INVALID, "apd_create: bad arguments");
+    CK(cudaSetDevice(device));
+    apd_ctx* c = new apd_ctx();
+    c->device = device;
+    c->sr = sample_rate;
+    c->C = chunk_samples;
+    c->n_clips = n_clips;
+    c->maxB = max_batch_chunks;
+    c->height = height_min > 0.0f ? height_min : kDefaultHeight;
+    std::string err;
+    if (!kw_config_create(sample_rate, &c->kw, &err)) { delete c; return fail(APD_ERR_UNSUPPORTED, err); }
+
+    // ---- clips and sliding-window groups (reference apd.py:155-161)
+    c->clips.resize(n_clips);
+    std::map<int, int> sw_to_group;
+    for (int p = 0; p < n_clips; ++p) {
+        ClipHost& cl = c->clips[p];
+        if (!descs[p].samples || descs[p].length <= 0) { delete c; return fail(APD_ERR_INVALID, "empty clip"); }
+        cl.L = descs[p].length;
+        cl.sw = (int)((cl.L + (long long)sample_rate - 1) / sample_rate);
+        if ((long long)2 * cl.sw * sample_rate > chunk_samples) {
+            delete c;
+            return fail(APD_ERR_INVALID, "seconds_per_chunk is too small for clip " + std::to_string(p));
+        }
+        cl.strategy = descs[p].strategy;
+        cl.tone_hz = descs[p].strategy == APD_STRATEGY_MARKER_TONE ? descs[p].tone_hz : 0.0;
+        cl.is_short = (2LL * cl.L < sample_rate) ? 1 : 0;             // L/sr < 0.5 (apd.py:628)
+        auto it = sw_to_group.find(cl.sw);
+        if (it == sw_to_group.end()) {
+            it = sw_to_group.emplace(cl.sw, (int)c->groups.size()).first;
+            Group g;
+            g.sw = cl.sw;
+            g.halo = cl.sw * sample_rate;
+            c->groups.push_back(g);
+        }
+        cl.group = it->second;
+        c->groups[cl.group].clips.push_back(p);
+        c->groups[cl.group].max_L = std::max(c->groups[cl.group].max_L, cl.L);
+    }
+    const int G = (int)c->groups.size();
+    long long max_nout = 0, max_M = 0;
+    int min_L = c->clips[0].L;
+    for (auto& cl : c->clips) min_L = std::min(min_L, cl.L);
+    for (auto& g : c->groups) {
+        const long long n_out = c->C + g.halo + g.max_L - 1;
+        max_nout = std::max(max_nout, n_out);
+        if (plan_min_M_for(n_out) > (1LL << 21) || !build_plan((int)plan_min_M_for(n_out), &g.plan, &err)) {
+            delete c;
+            return fail(APD_ERR_UNSUPPORTED, err.empty() ? "chunk too long for the FFT plan" : err);
+        }
+        g.spec_off = c->spec_slab;
+        c->spec_slab += g.plan.M;
+        max_M = std::max<long long>(max_M, g.plan.M);
+        CK(upload(&g.d_clips, g.clips));
+        CK(dalloc(&g.d_sel, (size_t)c->maxB * g.clips.size()));
+    }
+
+    // ---- pattern-side precompute on the device
+    unsigned int* d_tmp_max = nullptr;
+    int* d_tmp_int = nullptr;
+    float* d_zero_f = nullptr;
+    const float2** d_tmp_ptr = nullptr;
+    double *d_tl = nullptr, *d_tg = nullptr, *d_tstate = nullptr, *d_ten = nullptr, *d_tem1 = nullptr;
+    CK(dalloc(&d_tmp_max, 1));
+    CK(dalloc(&d_tmp_int, 2));
+    CK(cudaMemset(d_tmp_int, 0, 2 * sizeof(int)));
+    CK(dalloc(&d_zero_f, 1));
+    CK(cudaMemset(d_zero_f, 0, sizeof(float)));
+    CK(dalloc(&d_tmp_ptr, 1));
+    CK(dalloc(&d_tl, 1));
+    CK(dalloc(&d_tg, 1));
+    int max_L = 0;
+    for (auto& cl : c->clips) max_L = std::max(max_L, cl.L);
+    const int clip_cells = (max_L + c->kw.cell - 1) / c->kw.cell + 1;
+    CK(dalloc(&d_tstate, (size_t)clip_cells * 4));
+    CK(dalloc(&d_ten, (size_t)clip_cells));
+    CK(dalloc(&d_tem1, 1));
+    for (int p = 0; p < n_clips; ++p) {
+        ClipHost& cl = c->clips[p];
+        const int L = cl.L;
+        CK(dalloc(&cl.d_raw, (size_t)L));
+        CK(dalloc(&cl.d_norm, (size_t)L));
+        CK(dalloc(&cl.d_rev, (size_t)L));
+        CK(dalloc(&cl.d_self_corr, (size_t)2 * L - 1));
+        CK(cudaMemcpy(cl.d_raw, descs[p].samples, sizeof(float) * L, cudaMemcpyHostToDevice));
+        // loudness with block = clip_seconds if < 0.5 else 0.4 (apd.py:169-171): same rule as a section
+        SectionGeom Gc{cl.d_raw, 0, L, L, 0, 0};
+        launch_loudness(c->kw, Gc, 1, 0, clip_cells, d_tstate, d_ten, d_tem1, d_tl, d_tg, 1, 0);
+        k_prepare_clip<<<std::min(256, (L + 255) / 256), 256>>>(cl.d_raw, L, d_tg, cl.d_norm, cl.d_rev);
+        CK(cudaMemcpy(&cl.lufs, d_tl, sizeof(double), cudaMemcpyDeviceToHost));
+        c->launches += 5;
+        // spectrum of the reversed clip at the group's FFT size
+        Group& g = c->groups[cl.group];
+        CK(dalloc(&cl.d_spec, (size_t)g.plan.M));
+        {
+            float2* scr = nullptr;
+            CK(dalloc(&scr, (size_t)g.plan.M));
+            SectionGeom Gr{cl.d_rev, 0, L, L, 0, 0};
+            launch_forward(g.plan, Gr, nullptr, 0, 1, scr, cl.d_spec, g.plan.M, 0);
+            CK(cudaDeviceSynchronize());
+            cudaFree(scr);
+            c->launches += 2;
+        }
+        int rc = self_correlation(c, cl, d_tmp_max, d_tmp_int, d_zero_f, d_tmp_ptr);
+        if (rc != APD_OK) return rc;
+    }
+
+    // ---- per-clip tables
+    std::vector<int> h_len(n_clips), h_group(n_clips), h_strat(n_clips), h_short(n_clips), h_lo(n_clips * 3),
+        h_hi(n_clips * 3), h_ds(n_clips * 3, 0), h_P(n_clips, 0);
+    std::vector<float> h_smax(n_clips);
+    std::vector<const float*> h_cc(n_clips), h_cache(n_clips);
+    std::vector<const float2*> h_spec(n_clips);
+    std::vector<double> h_thz(n_clips), h_thr(n_clips * 6);
+    std::vector<const double2*> h_chirp(n_clips, nullptr), h_tw(n_clips, nullptr);
+    int max_P = 0;
+    for (int p = 0; p < n_clips; ++p) {
+        ClipHost& cl = c->clips[p];
+        const int L = cl.L, W = 2 * L - 1;
+        h_len[p] = L; h_group[p] = cl.group; h_strat[p] = cl.strategy; h_short[p] = cl.is_short;
+        h_smax[p] = cl.self_max; h_cc[p] = cl.d_self_corr; h_spec[p] = cl.d_spec; h_thz[p] = cl.tone_hz;
+        // Pearson windows (apd.py:808-829); bounds use Python's round(): half to even
+        const int wins[3][3] = {{0, 5, 252}, {4, 6, 101}, {5, 10, 252}};
+        int total_ds = 0;
+        if (cl.is_short) {
+            h_lo[p * 3] = (int)std::nearbyint((double)(W * 0LL) / 10.0);
+            h_hi[p * 3] = (int)std::nearbyint((double)((long long)W * 10) / 10.0);
+            h_ds[p * 3] = 505;
+            total_ds = 505;
+        } else {
+            for (int w = 0; w < 3; ++w) {
+                h_lo[p * 3 + w] = (int)std::nearbyint((double)((long long)W * wins[w][0]) / 10.0);
+                h_hi[p * 3 + w] = (int)std::nearbyint((double)((long long)W * wins[w][1]) / 10.0);
+                h_ds[p * 3 + w] = wins[w][2];
+                total_ds += wins[w][2];
+            }
+        }
+        CK(dalloc(&cl.d_win_cache, (size_t)total_ds));
+        int off = 0;
+        for (int w = 0; w < 3; ++w) {
+            if (h_ds[p * 3 + w] <= 0) continue;
+            k_window_max<<<4, 128>>>(cl.d_self_corr, h_lo[p * 3 + w], h_hi[p * 3 + w], h_ds[p * 3 + w], cl.d_win_cache + off);
+            off += h_ds[p * 3 + w];
+            ++c->launches;
+        }
+        h_cache[p] = cl.d_win_cache;
+        // marker-tone thresholds (apd.py:698-705) and Bluestein tables
+        const double defaults[6] = {0.95, 0.80, 9.0, 0.92, 0.25, 0.65};
+        const double given[6] = {descs[p].minimum_band_purity, descs[p].minimum_active_frame_ratio,
+                                 descs[p].minimum_longest_active_run, descs[p].minimum_active_frame_mean_purity,
+                                 descs[p].maximum_min_flank_purity, descs[p].maximum_max_flank_purity};
+        for (int k = 0; k < 6; ++k) h_thr[p * 6 + k] = given[k] == given[k] ? given[k] : defaults[k];
+        if (cl.strategy == APD_STRATEGY_MARKER_TONE && cl.tone_hz > 0.0) {
+            int P = 2;
+            while (P < 2 * L - 1) P <<= 1;
+            cl.tone_P = P;
+            max_P = std::max(max_P, P);
+            std::vector<double2> tw(P / 2);
+            for (int t = 0; t < P / 2; ++t) {
+                const double a = -2.0 * M_PI * (double)t / (double)P;
+                tw[t] = make_double2(cos(a), sin(a));
+            }
+            CK(upload(&cl.d_tone_tw, tw));
+            CK(dalloc(&cl.d_tone_chirp, (size_t)P));
+            double2 *b0 = nullptr, *b1 = nullptr;
+            CK(dalloc(&b0, (size_t)P));
+            CK(dalloc(&b1, (size_t)P));
+            launch_chirp_fft(L, P, cl.d_tone_tw, b0, b1, cl.d_tone_chirp, 0);
+            CK(cudaDeviceSynchronize());
+            cudaFree(b0);
+            cudaFree(b1);
+            ++c->launches;
+            h_P[p] = P; h_chirp[p] = cl.d_tone_chirp; h_tw[p] = cl.d_tone_tw;
+        }
+    }
+    CK(cudaDeviceSynchronize());
+    CK(upload(&c->d_clip_len, h_len));
+    CK(upload(&c->d_clip_group, h_group));
+    CK(upload(&c->d_strategy, h_strat));
+    CK(upload(&c->d_is_short, h_short));
+    CK(upload(&c->d_win_lo, h_lo));
+    CK(upload(&c->d_win_hi, h_hi));
+    CK(upload(&c->d_win_ds, h_ds));
+    CK(upload(&c->d_tone_P, h_P));
+    CK(upload(&c->d_self_max, h_smax));
+    CK(upload(&c->d_self_corr_ptrs, h_cc));
+    CK(upload(&c->d_win_cache_ptrs, h_cache));
+    CK(upload(&c->d_clip_spec_ptrs, h_spec));
+    CK(upload(&c->d_tone_hz, h_thz));
+    CK(upload(&c->d_tone_thr, h_thr));
+    CK(upload(&c->d_tone_chirp_ptrs, h_chirp));
+    CK(upload(&c->d_tone_tw_ptrs, h_tw));
+    cudaFree(d_tmp_max); cudaFree(d_tmp_int); cudaFree(d_zero_f); cudaFree((void*)d_tmp_ptr);
+    cudaFree(d_tl); cudaFree(d_tg); cudaFree(d_tstate); cudaFree(d_ten); cudaFree(d_tem1);
+
+    // ---- workspace
+    const int B = c->maxB;
+    CK(dalloc(&c->d_geoms, (size_t)G));
+    CK(cudaMallocHost((void**)&c->h_geoms, sizeof(SectionGeom) * G));
+    long long max_sec = c->C;
+    for (auto& g : c->groups) max_sec = std::max(max_sec, c->C + g.halo);
+    c->cells_stride = (int)((max_sec + c->kw.cell - 1) / c->kw.cell + 1);
+    CK(dalloc(&c->d_kw_state, (size_t)B * G * c->cells_stride * 4));
+    CK(dalloc(&c->d_kw_energy, (size_t)B * G * c->cells_stride));
+    CK(dalloc(&c->d_kw_em1, (size_t)B * G));
+    CK(dalloc(&c->d_lufs, (size_t)B * G));
+    CK(dalloc(&c->d_gain, (size_t)B * G));
+    CK(dalloc(&c->d_spec, (size_t)B * c->spec_slab));
+    c->inv_units = 512;
+    c->scratch_elems = std::max<long long>((long long)B, c->inv_units) * max_M;
+    CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
+    CK(dalloc(&c->d_unit_max, (size_t)B * n_clips));
+    CK(dalloc(&c->d_unit_npeaks, (size_t)B * n_clips));
+    CK(dalloc(&c->d_counts, (size_t)G + 4));
+    CK(cudaMallocHost((void**)&c->h_counts, sizeof(int) * (G + 4)));
+    c->n_slots = 256;
+    c->corr_stride = (max_nout + 31) / 32 * 32;
+    c->cand_stride = max_nout / 2 + 2;
+    c->peak_stride = (int)std::min<long long>(max_nout / std::max(min_L, 1) + 2, 8192);
+    CK(dalloc(&c->d_corr, (size_t)c->n_slots * c->corr_stride));
+    CK(dalloc(&c->d_cand_idx, (size_t)c->n_slots * c->cand_stride));
+    CK(dalloc(&c->d_cand_val, (size_t)c->n_slots * c->cand_stride));
+    CK(dalloc(&c->d_cand_state, (size_t)c->n_slots * c->cand_stride));
+    CK(dalloc(&c->d_peaks, (size_t)c->n_slots * c->peak_stride));
+    CK(dalloc(&c->d_n_peaks, (size_t)c->n_slots));
+    CK(dalloc(&c->d_n_cands, (size_t)c->n_slots));
+    CK(dalloc(&c->d_slot_cands, (size_t)c->n_slots * c->peak_stride));
+    c->out_capacity = std::max(4096, B * n_clips * 4);
+    CK(dalloc(&c->d_out, (size_t)c->out_capacity));
+    if (max_P > 0) {
+        c->tone_stride = max_P;
+        const long long per_cta = 3LL * 2 * max_P * (long long)sizeof(double2);
+        c->tone_ctas = (int)std::max<long long>(1, std::min<long long>(64, (1LL << 31) / per_cta));
+        CK(dalloc(&c->d_tone_scratch, (size_t)c->tone_ctas * 3 * 2 * max_P));
+        c->tone_item_cap = c->n_slots * 16;
+        CK(cudaMalloc(&c->d_tone_items, tone_item_bytes() * c->tone_item_cap));
+        CK(dalloc(&c->d_tone_metrics, (size_t)c->tone_item_cap * 15));
+        const double wlr = std::nearbyint(0.025 * (double)sample_rate);
+        c->tone_wl = wlr > 32.0 ? (int)wlr : 32;
+    }
+    CK(cudaDeviceSynchronize());
+    *out = c;
+    return APD_OK;
+}
+
+extern "C" int apd_destroy(apd_ctx* c)
+{
+    if (!c) return APD_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& cl : c->clips) {
+        cudaFree(cl.d_raw); cudaFree(cl.d_norm); cudaFree(cl.d_rev); cudaFree(cl.d_spec);
+        cudaFree(cl.d_self_corr); cudaFree(cl.d_win_cache); cudaFree(cl.d_tone_chirp); cudaFree(cl.d_tone_tw);
+    }
+    for (auto& g : c->groups) { free_plan(&g.plan); cudaFree(g.d_clips); cudaFree(g.d_sel); }
+    for (auto& kv : c->self_plans) free_plan(&kv.second);
+    kw_config_destroy(&c->kw);
+    void* ptrs[] = {c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
+                    c->d_win_ds, c->d_tone_P, c->d_self_max, (void*)c->d_self_corr_ptrs, (void*)c->d_win_cache_ptrs,
+                    (void*)c->d_clip_spec_ptrs, c->d_tone_hz, c->d_tone_thr, (void*)c->d_tone_chirp_ptrs,
+                    (void*)c->d_tone_tw_ptrs, c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
+                    c->d_gain, c->d_spec, c->d_scratch, c->d_unit_max, c->d_unit_npeaks, c->d_counts, c->d_corr,
+                    c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
+                    c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics};
+    for (void* p : ptrs) cudaFree(p);
+    cudaFreeHost(c->h_geoms);
+    cudaFreeHost(c->h_counts);
+    delete c;
+    return APD_OK;
+}
+
+extern "C" int apd_clip_info(apd_ctx* c, int clip, int32_t* sw, double* lufs, float* self_max, int32_t* fft_points)
+{
+    if (!c || clip < 0 || clip >= c->n_clips) return fail(APD_ERR_INVALID, "apd_clip_info: bad clip");
+    const ClipHost& cl = c->clips[clip];
+    if (sw) *sw = cl.sw;
+    if (lufs) *lufs = cl.lufs;
+    if (self_max) *self_max = cl.self_max;
+    if (fft_points) *fft_points = 2 * c->groups[cl.group].plan.M;
+    return APD_OK;
+}
+
+extern "C" int apd_clip_normalized(apd_ctx* c, int clip, float* out_host)
+{
+    if (!c || clip < 0 || clip >= c->n_clips || !out_host) return fail(APD_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(out_host, c->clips[clip].d_norm, sizeof(float) * c->clips[clip].L, cudaMemcpyDeviceToHost));
+    return APD_OK;
+}
+
+extern "C" int apd_clip_self_correlation(apd_ctx* c, int clip, float* out_host)
+{
+    if (!c || clip < 0 || clip >= c->n_clips || !out_host) return fail(APD_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(out_host, c->clips[clip].d_self_corr, sizeof(float) * (2 * c->clips[clip].L - 1),
+                  cudaMemcpyDeviceToHost));
+    return APD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------
+static int stage_begin(apd_ctx* c, const float* audio, int64_t base, int64_t n, int cb, int ce, cudaStream_t st)
+{
+    if (!c || !audio || n <= 0 || ce <= cb || cb < 0) return fail(APD_ERR_INVALID, "scan: bad arguments");
+    if (ce - cb > c->maxB) return fail(APD_ERR_INVALID, "scan: more chunks than max_batch_chunks");
+    int max_halo = 0;
+    for (auto& g : c->groups) max_halo = std::max(max_halo, g.halo);
+    if (cb > 0 && (long long)cb * c->C - max_halo < base)
+        return fail(APD_ERR_INVALID, "scan: audio region does not contain the look-back halo of chunk_begin");
+    if (cb == 0 && base != 0) return fail(APD_ERR_INVALID, "scan: chunk 0 requires base_sample == 0");
+    if ((long long)(ce - 1) * c->C >= base + n) return fail(APD_ERR_INVALID, "scan: chunk_end beyond the audio region");
+    CK(cudaSetDevice(c->device));
+    c->audio = audio; c->base = base; c->nsamp = n; c->chunk_begin = cb; c->chunk_end = ce;
+    fill_geoms(c);
+    CK(cudaMemcpyAsync(c->d_geoms, c->h_geoms, sizeof(SectionGeom) * c->groups.size(), cudaMemcpyHostToDevice, st));
+    const int B = ce - cb;
+    CK(cudaMemsetAsync(c->d_unit_max, 0, sizeof(unsigned int) * (size_t)B * c->n_clips, st));
+    CK(cudaMemsetAsync(c->d_unit_npeaks, 0xff, sizeof(int) * (size_t)B * c->n_clips, st));
+    CK(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * (c->groups.size() + 4), st));
+    c->staged = true;
+    return APD_OK;
+}
+
+static int stage_loudness(apd_ctx* c, cudaStream_t st)
+{
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
+    for (int g = 0; g < G; ++g) {
+        launch_loudness(c->kw, c->h_geoms[g], B, g * B, c->cells_stride, c->d_kw_state, c->d_kw_energy,
+                        c->d_kw_em1, c->d_lufs + g, c->d_gain + g, G, st);
+        c->launches += 4;
+    }
+    CK(cudaGetLastError());
+    return APD_OK;
+}
+
+static int stage_forward(apd_ctx* c, cudaStream_t st)
+{
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
+    for (int g = 0; g < G; ++g) {
+        Group& gr = c->groups[g];
+        launch_forward(gr.plan, c->h_geoms[g], c->d_gain + g, G, B, c->d_scratch, c->d_spec + gr.spec_off,
+                       c->spec_slab, st);
+        c->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return APD_OK;
+}
+
+static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
+{
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
+    InvOut O{c->d_unit_max, c->n_clips, nullptr, 0, c->d_self_max, c->d_clip_len};
+    for (int g = 0; g < G; ++g) {
+        Group& gr = c->groups[g];
+        const int ng = (int)gr.clips.size();
+        const int nunits = B * ng;
+        for (int u0 = 0; u0 < nunits; u0 += c->inv_units) {
+            UnitSrc U{nullptr, gr.d_clips, ng, u0};
+            launch_inverse_max(gr.plan, c->h_geoms[g], c->d_spec + gr.spec_off, c->spec_slab, U,
+                               std::min(c->inv_units, nunits - u0), c->d_clip_spec_ptrs, c->d_scratch, O, st);
+            c->launches += 2;
+        }
+    }
+    CK(cudaGetLastError());
+    return APD_OK;
+}
+
+static int stage_peaks_verify(apd_ctx* c, cudaStream_t st)
+{
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
+    for (int g = 0; g < G; ++g) {
+        Group& gr = c->groups[g];
+        k_select_group<<<1, 1024, 0, st>>>(c->d_unit_max, c->d_self_max, gr.d_clips, (int)gr.clips.size(),
+                                           c->n_clips, B, c->height, gr.d_sel, c->d_counts + g);
+        ++c->launches;
+    }
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int g = 0; g < G; ++g) {
+        Group& gr = c->groups[g];
+        const int cnt = c->h_counts[g];
+        for (int u0 = 0; u0 < cnt; u0 += c->n_slots) {
+            const int ns = std::min(c->n_slots, cnt - u0);
+            UnitSrc U{gr.d_sel, nullptr, 0, u0};
+            InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max, c->d_clip_len};
+            launch_inverse_write(gr.plan, c->h_geoms[g], c->d_spec + gr.spec_off, c->spec_slab, U, ns,
+                                 c->d_clip_spec_ptrs, c->d_scratch, O, st);
+            c->launches += 2;
+            PeakArgs PA{gr.d_sel, c->d_counts + g, u0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
+                        c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
+                        c->d_peaks, c->peak_stride, c->d_n_peaks, c->d_n_cands, c->d_counts + G + 1};
+            launch_find_peaks(PA, ns, st);
+            ++c->launches;
+            ClipVerify CV{c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_self_corr_ptrs, c->d_win_lo,
+                          c->d_win_hi, c->d_win_ds, c->d_win_cache_ptrs, c->d_is_short, c->d_tone_hz, c->d_tone_thr,
+                          c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs};
+            VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + G, c->out_capacity,
+                          c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
+            launch_verify(VA, ns, st, &c->launches);
+            bool group_has_tone = false;
+            for (int p : gr.clips)
+                group_has_tone |= c->clips[p].strategy == APD_STRATEGY_MARKER_TONE && c->clips[p].tone_hz > 0.0;
+            if (group_has_tone)
+                launch_tone(VA, ns, c->d_tone_items, c->d_counts + G + 2, c->tone_item_cap, c->d_tone_metrics,
+                            c->tone_ctas, c->tone_wl, st, &c->launches);
+            launch_emit(VA, ns, st, &c->launches);
+            k_record_npeaks<<<(ns + 127) / 128, 128, 0, st>>>(gr.d_sel, c->d_counts + g, u0, ns, c->d_n_peaks,
+                                                             c->n_clips, c->d_unit_npeaks);
+            ++c->launches;
+        }
+    }
+    CK(cudaGetLastError());
+    return APD_OK;
+}
+
+extern "C" int apd_stage_loudness(apd_ctx* c, const float* audio, int64_t base, int64_t n, int32_t cb, int32_t ce,
+                                  void* stream)
+{
+    int rc = stage_begin(c, audio, base, n, cb, ce, (cudaStream_t)stream);
+    if (rc) return rc;
+    return stage_loudness(c, (cudaStream_t)stream);
+}
+extern "C" int apd_stage_forward_fft(apd_ctx* c, void* stream)
+{
+    if (!c || !c->staged) return fail(APD_ERR_INVALID, "no staged batch");
+    return stage_forward(c, (cudaStream_t)stream);
+}
+extern "C" int apd_stage_correlate_max(apd_ctx* c, void* stream)
+{
+    if (!c || !c->staged) return fail(APD_ERR_INVALID, "no staged batch");
+    return stage_correlate_max(c, (cudaStream_t)stream);
+}
+extern "C" int apd_stage_peaks_verify(apd_ctx* c, void* stream)
+{
+    if (!c || !c->staged) return fail(APD_ERR_INVALID, "no staged batch");
+    return stage_peaks_verify(c, (cudaStream_t)stream);
+}
+
+static bool cand_less(const apd_candidate& a, const apd_candidate& b)
+{
+    if (a.chunk != b.chunk) return a.chunk < b.chunk;
+    if (a.clip != b.clip) return a.clip < b.clip;
+    return a.peak < b.peak;
+}
+
+static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
+                   double* lufs_host, cudaStream_t st)
+{
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (G + 4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int n = c->h_counts[G];
+    if (c->h_counts[G + 1]) return fail(APD_ERR_OVERFLOW, "candidate workspace overflow (flags " +
+                                        std::to_string(c->h_counts[G + 1]) + ")");
+    if (n > cap) return fail(APD_ERR_OVERFLOW, "candidate buffer too small");
+    if (n > 0) {
+        CK(cudaMemcpyAsync(cand_host, c->d_out, sizeof(apd_candidate) * n, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<unsigned int> um;
+    std::vector<int> np;
+    if (trace) {
+        um.resize((size_t)B * c->n_clips);
+        np.resize((size_t)B * c->n_clips);
+        CK(cudaMemcpyAsync(um.data(), c->d_unit_max, sizeof(unsigned int) * um.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(np.data(), c->d_unit_npeaks, sizeof(int) * np.size(), cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<double> lf;
+    if (lufs_host) {
+        lf.resize((size_t)B * G);
+        CK(cudaMemcpyAsync(lf.data(), c->d_lufs, sizeof(double) * lf.size(), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    std::sort(cand_host, cand_host + n, cand_less);
+    *n_cand = n;
+    if (trace) {
+        for (int ci = 0; ci < B; ++ci)
+            for (int p = 0; p < c->n_clips; ++p) {
+                apd_unit_trace& t = trace[(size_t)ci * c->n_clips + p];
+                float am;
+                memcpy(&am, &um[(size_t)ci * c->n_clips + p], sizeof(float));
+                t.absmax = am;
+                t.max_choose = std::max(c->clips[p].self_max, am);
+                long long s;
+                int ns;
+                section_bounds(c->h_geoms[c->clips[p].group], ci, s, ns);
+                t.n_out = ns > 0 ? ns + c->clips[p].L - 1 : 0;
+                t.n_peaks = np[(size_t)ci * c->n_clips + p];
+            }
+    }
+    if (lufs_host)
+        for (int ci = 0; ci < B; ++ci)
+            for (int p = 0; p < c->n_clips; ++p)
+                lufs_host[(size_t)ci * c->n_clips + p] = lf[(size_t)ci * G + c->clips[p].group];
+    return APD_OK;
+}
+
+extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n, int32_t cb, int32_t ce,
+                        apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
+                        double* lufs_host, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null output");
+    int rc = stage_begin(c, audio, base, n, cb, ce, st);
+    if (rc) return rc;
+    if ((rc = stage_loudness(c, st))) return rc;
+    if ((rc = stage_forward(c, st))) return rc;
+    if ((rc = stage_correlate_max(c, st))) return rc;
+    if ((rc = stage_peaks_verify(c, st))) return rc;
+    return collect(c, cand_host, cap, n_cand, trace, lufs_host, st);
+}
+
+extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t clip, float* out_host, int32_t capacity,
+                                          int32_t* n_out, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!c || !c->staged || clip < 0 || clip >= c->n_clips || chunk < c->chunk_begin || chunk >= c->chunk_end)
+        return fail(APD_ERR_INVALID, "unit_correlation: bad unit");
+    const ClipHost& cl = c->clips[clip];
+    Group& gr = c->groups[cl.group];
+    long long s;
+    int ns;
+    section_bounds(c->h_geoms[cl.group], chunk - c->chunk_begin, s, ns);
+    const int no = ns > 0 ? ns + cl.L - 1 : 0;
+    if (no > capacity) return fail(APD_ERR_INVALID, "unit_correlation: buffer too small");
+    int2 u = make_int2(chunk - c->chunk_begin, clip);
+    int2* d_u = nullptr;
+    CK(dalloc(&d_u, 1));
+    CK(cudaMemcpyAsync(d_u, &u, sizeof(u), cudaMemcpyHostToDevice, st));
+    UnitSrc U{d_u, nullptr, 0, 0};
+    InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max, c->d_clip_len};
+    launch_inverse_write(gr.plan, c->h_geoms[cl.group], c->d_spec + gr.spec_off, c->spec_slab, U, 1,
+                         c->d_clip_spec_ptrs, c->d_scratch, O, st);
+    c->launches += 2;
+    CK(cudaMemcpyAsync(out_host, c->d_corr, sizeof(float) * no, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_u);
+    *n_out = no;
+    return APD_OK;
+}
+
+extern "C" int64_t apd_launch_count(apd_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int apd_unit_n_out(apd_ctx* c, int32_t chunk, int32_t clip, int64_t total_samples, int32_t* n_out)
+{
+    if (!c || clip < 0 || clip >= c->n_clips || !n_out) return fail(APD_ERR_INVALID, "bad arguments");
+    SectionGeom G{nullptr, 0, total_samples, c->C, 0, c->groups[c->clips[clip].group].halo};
+    long long s;
+    int ns;
+    section_bounds(G, chunk, s, ns);
+    *n_out = ns > 0 ? ns + c->clips[clip].L - 1 : 0;
+    return APD_OK;
+}

@@ -1,0 +1,329 @@
+// Four-step real FFT cross-correlation kernels (Step 1 of the detection path).
+//
+// Replaces fft_correlation.fft_correlate_1d(section, clip, 'full') + abs + max
+// (reference audio_pattern_detector.py:487-494) for a whole batch of
+// (chunk x pattern) units at once.
+//
+// Real transform trick (no mirrored-bin pass): for a real x of length N = 2M,
+//     u[m] = (x[m] - i x[m+M]) * e^{-i pi m / N},   U = FFT_M(u)
+// gives the odd-frequency spectrum X_o[2g] = U[g].  Point-wise products of two
+// such spectra are the spectrum of the *negacyclic* convolution, which equals
+// the linear one because N >= S + L - 1.  The inverse undoes the same steps:
+//     v = IFFT_M(U_a U_b),  z = v[m] e^{+i pi m / N},  y[m] = Re z, y[m+M] = -Im z.
+//
+// Complex FFT_M with M = N1*N2 is done as two tiled passes ("four-step"):
+//   forward : column pass (N1-point FFTs over a tile of TB adjacent columns, fused with the
+//             section load: loudness gain, clip, NaN scrub, packing, pre-twiddle) -> twiddle
+//             -> row pass (N2-point FFTs) ; spectrum stored as [c][d], frequency g = c + N1 d.
+//   inverse : row pass (fused spectral multiply) -> twiddle -> column pass (fused post-twiddle,
+//             |.|, per-unit max or normalised write-out).
+// Every global access of every pass is a contiguous run of >= 32 bytes.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "internal.h"
+
+namespace apd {
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(512)
+k_fwd_cols(Fft4Plan P, SectionGeom G, const double* __restrict__ gains, int gain_stride, float2* __restrict__ T)
+{
+    extern __shared__ float2 smem[];
+    const int TB = 1 << P.tb_log2;
+    float2* A = smem;
+    float2* B = smem + P.N1 * TB;
+    const int sec = blockIdx.y;
+    const int b0 = blockIdx.x * TB;
+    long long start;
+    int n;
+    section_bounds(G, sec, start, n);
+    const float* __restrict__ x = G.audio + (start - G.base);
+    const double gain = gains ? gains[(long long)sec * gain_stride] : 1.0;
+    const int M = P.M;
+    const float invN = 1.0f / (2.0f * (float)M);
+    const int total = P.N1 << P.tb_log2;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int q = idx & (TB - 1);
+        const int a = idx >> P.tb_log2;
+        const int m = a * P.N2 + b0 + q;
+        const float x0 = m < n ? normalize_sample(x[m], gain) : 0.0f;
+        const float x1 = m + M < n ? normalize_sample(x[m + M], gain) : 0.0f;
+        A[idx] = cmul(make_float2(x0, -x1), cispif(-(float)m * invN));
+    }
+    __syncthreads();
+    const float2* R = sub_fft<-1>(P.col, A, B, P.tb_log2, TB);
+    const float invM = 1.0f / (float)M;
+    float2* __restrict__ out = T + (long long)sec * M;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int q = idx & (TB - 1);
+        const int c = idx >> P.tb_log2;
+        const int b = b0 + q;
+        out[c * P.N2 + b] = cmul(R[idx], twiddle_frac(b * c, invM, -1.0f));
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_fwd_rows(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ spec, long long spec_stride)
+{
+    extern __shared__ float2 smem[];
+    const int TR = 1 << P.tr_log2;
+    const int LD = TR + 1;
+    float2* A = smem;
+    float2* B = smem + P.N2 * LD;
+    const int sec = blockIdx.y;
+    const int c0 = blockIdx.x * TR;
+    const float2* __restrict__ in = T + (long long)sec * P.M + (long long)c0 * P.N2;
+    const int total = P.N2 << P.tr_log2;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int e = idx & (P.N2 - 1);
+        const int q = idx / P.N2;
+        A[e * LD + q] = in[q * P.N2 + e];
+    }
+    __syncthreads();
+    const float2* R = sub_fft<-1>(P.row, A, B, P.tr_log2, LD);
+    float2* __restrict__ out = spec + (long long)sec * spec_stride + (long long)c0 * P.N2;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int d = idx & (P.N2 - 1);
+        const int q = idx / P.N2;
+        out[q * P.N2 + d] = R[d * LD + q];
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_inv_rows(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U,
+           const float2* const* __restrict__ clip_spec, float2* __restrict__ W)
+{
+    extern __shared__ float2 smem[];
+    const int TR = 1 << P.tr_log2;
+    const int LD = TR + 1;
+    float2* A = smem;
+    float2* B = smem + P.N2 * LD;
+    const int u = blockIdx.y;
+    const int2 unit = get_unit(U, u);
+    const int c0 = blockIdx.x * TR;
+    const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + (long long)c0 * P.N2;
+    const float2* __restrict__ hs = clip_spec[unit.y] + (long long)c0 * P.N2;
+    const int total = P.N2 << P.tr_log2;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int e = idx & (P.N2 - 1);
+        const int q = idx / P.N2;
+        A[e * LD + q] = cmul(xs[q * P.N2 + e], __ldg(&hs[q * P.N2 + e]));
+    }
+    __syncthreads();
+    const float2* R = sub_fft<+1>(P.row, A, B, P.tr_log2, LD);
+    const float invM = 1.0f / (float)P.M;
+    float2* __restrict__ out = W + (long long)u * P.M + (long long)c0 * P.N2;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int b = idx & (P.N2 - 1);
+        const int q = idx / P.N2;
+        out[q * P.N2 + b] = cmul(R[b * LD + q], twiddle_frac(b * (c0 + q), invM, +1.0f));
+    }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(512)
+k_inv_cols(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, InvOut O)
+{
+    extern __shared__ float2 smem[];
+    __shared__ float red[16];
+    const int TB = 1 << P.tb_log2;
+    float2* A = smem;
+    float2* B = smem + P.N1 * TB;
+    const int u = blockIdx.y;
+    const int2 unit = get_unit(U, u);
+    const int b0 = blockIdx.x * TB;
+    const int M = P.M;
+    const float2* __restrict__ in = W + (long long)u * M;
+    const int total = P.N1 << P.tb_log2;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int q = idx & (TB - 1);
+        const int c = idx >> P.tb_log2;
+        A[idx] = in[c * P.N2 + b0 + q];
+    }
+    __syncthreads();
+    const float2* R = sub_fft<+1>(P.col, A, B, P.tb_log2, TB);
+
+    long long start;
+    int n;
+    section_bounds(G, unit.x, start, n);
+    const int n_out = n > 0 ? n + O.clip_len[unit.y] - 1 : 0;
+    const float invN = 1.0f / (2.0f * (float)M);
+    const float invM = 1.0f / (float)M;
+    float mc = 1.0f;
+    if (WRITE) {
+        const float um = __uint_as_float(O.unit_max_bits[(long long)unit.x * O.n_clips + unit.y]);
+        mc = fmaxf(O.self_max[unit.y], um);                       // apd.py:493
+    }
+    float* __restrict__ corr = WRITE ? O.corr + (long long)u * O.corr_stride : nullptr;
+    float best = 0.0f;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int q = idx & (TB - 1);
+        const int a = idx >> P.tb_log2;
+        const int m = a * P.N2 + b0 + q;
+        const float2 z = cmul(R[idx], cispif((float)m * invN));
+        const float y0 = fabsf(z.x * invM);
+        const float y1 = fabsf(z.y * invM);
+        if (WRITE) {
+            if (m < n_out) corr[m] = y0 / mc;                      // apd.py:494 (float32 divide)
+            if (m + M < n_out) corr[m + M] = y1 / mc;
+        } else {
+            if (m < n_out) best = fmaxf(best, y0);
+            if (m + M < n_out) best = fmaxf(best, y1);
+        }
+    }
+    if (!WRITE) {
+        best = warp_max(best);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+            v = warp_max(v);
+            if (threadIdx.x == 0)
+                atomicMax(&O.unit_max_bits[(long long)unit.x * O.n_clips + unit.y], __float_as_uint(v));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ plans
+static bool factor(int n, SubPlan* sp)
+{
+    sp->n = n;
+    sp->npass = 0;
+    int rest = n;
+    int odd[kMaxPasses];
+    int nodd = 0;
+    while (rest % 5 == 0) { if (nodd >= kMaxPasses) return false; odd[nodd++] = 5; rest /= 5; }
+    while (rest % 3 == 0) { if (nodd >= kMaxPasses) return false; odd[nodd++] = 3; rest /= 3; }
+    while (rest % 8 == 0) { if (sp->npass >= kMaxPasses) return false; sp->radix[sp->npass++] = 8; rest /= 8; }
+    if (rest % 4 == 0) { if (sp->npass >= kMaxPasses) return false; sp->radix[sp->npass++] = 4; rest /= 4; }
+    if (rest % 2 == 0) { if (sp->npass >= kMaxPasses) return false; sp->radix[sp->npass++] = 2; rest /= 2; }
+    if (rest != 1) return false;
+    for (int i = 0; i < nodd; ++i) {
+        if (sp->npass >= kMaxPasses) return false;
+        sp->radix[sp->npass++] = odd[i];
+    }
+    return true;
+}
+
+static bool upload_twiddles(SubPlan* sp)
+{
+    std::vector<float2> h(sp->n);
+    for (int t = 0; t < sp->n; ++t) {
+        const double ang = -2.0 * M_PI * (double)t / (double)sp->n;
+        h[t] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    float2* d = nullptr;
+    if (cudaMalloc(&d, sizeof(float2) * sp->n) != cudaSuccess) return false;
+    if (cudaMemcpy(d, h.data(), sizeof(float2) * sp->n, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    sp->tw = d;
+    return true;
+}
+
+long long plan_min_M_for(long long n_out) { return (n_out + 1) / 2; }
+
+bool build_plan(int M_min, Fft4Plan* plan, std::string* err)
+{
+    // candidate column lengths: 2^a * 3^b * 5^c, a >= 3, b <= 2, c <= 1
+    std::vector<int> n1s;
+    for (int a = 3; a <= 11; ++a)
+        for (int b = 0; b <= 2; ++b)
+            for (int c = 0; c <= 1; ++c) {
+                long long v = (1LL << a);
+                for (int i = 0; i < b; ++i) v *= 3;
+                for (int i = 0; i < c; ++i) v *= 5;
+                if (v <= 2048) n1s.push_back((int)v);
+            }
+    double best_cost = 1e300;
+    int bN1 = 0, bN2 = 0;
+    for (int n2 = 32; n2 <= 1024; n2 *= 2)
+        for (int n1 : n1s) {
+            const long long M = (long long)n1 * n2;
+            if (M < M_min) continue;
+            const double skew = std::fabs(std::log2((double)n1 / (double)n2));
+            const double cost = (double)M * (1.0 + 0.03 * skew);
+            if (cost < best_cost) { best_cost = cost; bN1 = n1; bN2 = n2; }
+        }
+    if (!bN1) {
+        if (err) *err = "section + clip too long for the four-step FFT (max 2^22 real samples)";
+        return false;
+    }
+    Fft4Plan P;
+    P.N1 = bN1; P.N2 = bN2; P.M = bN1 * bN2;
+    if (!factor(P.N1, &P.col) || !factor(P.N2, &P.row)) {
+        if (err) *err = "internal: cannot factor sub-FFT length";
+        return false;
+    }
+    // column tile: as wide as fits ~96 KB for both ping-pong buffers, 4..32 columns
+    int tb = 5;
+    while (tb > 2 && (size_t)2 * P.N1 * (1u << tb) * sizeof(float2) > 96u * 1024u) --tb;
+    P.tb_log2 = tb;
+    int tr = 3;
+    while (tr > 2 && (size_t)2 * P.N2 * ((1u << tr) + 1) * sizeof(float2) > 96u * 1024u) --tr;
+    P.tr_log2 = tr;
+    P.smem_col = (size_t)2 * P.N1 * (1u << P.tb_log2) * sizeof(float2);
+    P.smem_row = (size_t)2 * P.N2 * ((1u << P.tr_log2) + 1) * sizeof(float2);
+    P.threads = 256;
+    if (!upload_twiddles(&P.col) || !upload_twiddles(&P.row)) {
+        if (err) *err = "cudaMalloc failed for twiddle tables";
+        return false;
+    }
+    *plan = P;
+    return true;
+}
+
+void free_plan(Fft4Plan* plan)
+{
+    if (plan->col.tw) cudaFree((void*)plan->col.tw);
+    if (plan->row.tw) cudaFree((void*)plan->row.tw);
+    plan->col.tw = plan->row.tw = nullptr;
+}
+
+// ------------------------------------------------------------------ launchers
+static void ensure_attrs()
+{
+    static bool done = false;
+    if (done) return;
+    const int big = 200 * 1024;
+    cudaFuncSetAttribute(k_fwd_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_fwd_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_inv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_inv_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_inv_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    done = true;
+}
+
+void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains, int gain_stride, int nsec,
+                    float2* scratch, float2* spec, long long spec_stride, cudaStream_t st)
+{
+    if (nsec <= 0) return;
+    ensure_attrs();
+    dim3 gc(P.N2 >> P.tb_log2, nsec), gr(P.N1 >> P.tr_log2, nsec);
+    k_fwd_cols<<<gc, P.threads, P.smem_col, st>>>(P, G, gains, gain_stride, scratch);
+    k_fwd_rows<<<gr, P.threads, P.smem_row, st>>>(P, scratch, spec, spec_stride);
+}
+
+void launch_inverse_max(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
+                        const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch,
+                        const InvOut& out, cudaStream_t st)
+{
+    if (nunits <= 0) return;
+    ensure_attrs();
+    dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);
+    k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
+    k_inv_cols<false><<<gc, P.threads, P.smem_col, st>>>(P, G, U, scratch, out);
+}
+
+void launch_inverse_write(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
+                          const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch,
+                          const InvOut& out, cudaStream_t st)
+{
+    if (nunits <= 0) return;
+    ensure_attrs();
+    dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);
+    k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
+    k_inv_cols<true><<<gc, P.threads, P.smem_col, st>>>(P, G, U, scratch, out);
+}
+
+}  // namespace apd

@@ -1,0 +1,84 @@
+// Internal structures shared by the kernels and the C-ABI layer (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "fft_sub.cuh"
+
+namespace apd {
+
+// ---------------------------------------------------------------------------
+// Four-step FFT plan for a complex transform of M = N1 * N2 points, used for a
+// real (negacyclic, odd-frequency) transform of N = 2M points.  See fft4.cu.
+// ---------------------------------------------------------------------------
+struct Fft4Plan {
+    int M = 0, N1 = 0, N2 = 0;
+    SubPlan col{};          // length N1 (column passes)
+    SubPlan row{};          // length N2 (row passes)
+    int tb_log2 = 0;        // column tile width  TB = 1 << tb_log2 (adjacent columns per CTA)
+    int tr_log2 = 0;        // row tile height    TR = 1 << tr_log2 (adjacent rows per CTA)
+    int threads = 256;
+    size_t smem_col = 0, smem_row = 0;
+};
+
+// Where section `ci` (chunk chunk0+ci, look-back `halo`) lives inside the device-resident stream.
+struct SectionGeom {
+    const float* audio;     // audio[0] is stream sample `base`
+    long long base;         // global index of audio[0]
+    long long total;        // global index one past the last available sample
+    long long chunk;        // samples per chunk C
+    int chunk0;             // global index of the batch's first chunk
+    int halo;               // look-back samples for this group (sliding_window * sr)
+};
+
+__host__ __device__ inline void section_bounds(const SectionGeom& g, int ci, long long& start_abs, int& n)
+{
+    const long long i = (long long)g.chunk0 + ci;
+    start_abs = i * g.chunk - (i > 0 ? (long long)g.halo : 0LL);     // apd.py:406-412
+    long long end_abs = (i + 1) * g.chunk;
+    if (end_abs > g.total) end_abs = g.total;
+    n = end_abs > start_abs ? (int)(end_abs - start_abs) : 0;
+}
+
+// How the CTAs of an inverse launch find their (section, clip) unit.
+struct UnitSrc {
+    const int2* list;        // explicit (ci, clip) pairs, or nullptr for the dense layout below
+    const int* group_clips;  // dense: clip = group_clips[u % ng], ci = u / ng
+    int ng;
+    int u0;                  // first unit of this launch (offset into list / dense numbering)
+};
+
+__device__ __forceinline__ int2 get_unit(const UnitSrc& s, int u)
+{
+    u += s.u0;
+    if (s.list) return s.list[u];
+    return make_int2(u / s.ng, s.group_clips[u % s.ng]);
+}
+
+struct InvOut {
+    // phase 1: per-unit maximum of |corr| (float bits, atomicMax), indexed ci * n_clips + clip
+    unsigned int* unit_max_bits;
+    int n_clips;
+    // phase 2: normalised correlation written to slot (launch-local unit index), stride in floats
+    float* corr;
+    long long corr_stride;
+    const float* self_max;   // per clip
+    const int* clip_len;     // per clip
+};
+
+bool build_plan(int M_min, Fft4Plan* plan, std::string* err);                 // picks N1, N2 >= M_min
+void free_plan(Fft4Plan* plan);
+long long plan_min_M_for(long long n_out);
+
+void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains, int gain_stride, int nsec,
+                    float2* scratch /* nsec*M */, float2* spec, long long spec_stride, cudaStream_t st);
+void launch_inverse_max(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
+                        const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch /* nunits*M */,
+                        const InvOut& out, cudaStream_t st);
+void launch_inverse_write(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
+                          const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch,
+                          const InvOut& out, cudaStream_t st);
+
+}  // namespace apd

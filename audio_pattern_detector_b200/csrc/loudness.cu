@@ -1,0 +1,329 @@
+// K0: BS.1770-4 gated integrated loudness of every section of a batch -> normalisation gain.
+//
+// Replaces native-helper integrated_loudness (reference lib.rs:75-214) +
+// the gain of loudness_normalize (lib.rs:220-223) as called at
+// audio_pattern_detector.py:414-420 (sections) and :166-171 (clips).
+//
+// The reference runs the two K-weighting biquads as ONE serial float64 recurrence
+// over the whole section.  Here the section is cut into cells of `cell` samples
+// (cell divides the 100 ms gating hop):
+//   pass A  every cell is filtered from zero state        -> end state z_i   (parallel)
+//   scan    s_i = Mc s_{i-1} + z_i, Mc = A^cell (4x4)     -> true carry-in   (warp scan)
+//   pass B  every cell is filtered again from its carry   -> cell energy E_i (parallel)
+//   gate    400 ms blocks = 4*k consecutive cells, absolute (-70 LUFS) and relative
+//           (-10 LU) gates, LUFS, gain = 10^((-16 - LUFS)/20)        (one warp per section)
+// which is the same linear recurrence re-associated, all in float64.
+//
+// Restriction: the gating hop 0.1*sr must be an integer number of samples
+// (sr % 10 == 0) so that block edges fall on cell edges; apd_create rejects other rates.
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+#include "loudness.h"
+
+namespace apd {
+
+__device__ __forceinline__ void kw_step(const double* cf, double x, double& s1, double& s2, double& h1,
+                                        double& h2, double& v)
+{
+    const double u = cf[0] * x + s1;
+    s1 = cf[1] * x - cf[4] * u + s2;
+    s2 = cf[2] * x - cf[5] * u;
+    v = cf[6] * u + h1;
+    h1 = cf[7] * u - cf[10] * v + h2;
+    h2 = cf[8] * u - cf[11] * v;
+}
+
+// PASS 0: zero-state run, writes end state into state[sec][cell][4].
+// PASS 1: run from state[sec][cell] (carry-in), writes energy[sec][cell]
+//         (and energy_m1[sec] = energy of the last cell without its final sample).
+template <int PASS>
+__global__ void __launch_bounds__(128)
+k_kw_cells(KwConfig K, SectionGeom G, int sec0, int cells_stride, double* __restrict__ state,
+           double* __restrict__ energy, double* __restrict__ energy_m1)
+{
+    extern __shared__ float tile[];
+    const int sec = blockIdx.y;
+    long long start;
+    int n;
+    section_bounds(G, sec, start, n);
+    const int cell = K.cell;
+    const int first = blockIdx.x * blockDim.x;              // first cell of this CTA
+    const long long s0 = (long long)first * cell;           // first sample (section relative)
+    if (s0 >= n) return;
+    const int cnt = (int)min((long long)blockDim.x * cell, (long long)n - s0);
+    const float* __restrict__ x = G.audio + (start - G.base) + s0;
+    const int ld = cell + 1;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) tile[(i / cell) * ld + (i % cell)] = x[i];
+    __syncthreads();
+    const int ci = first + threadIdx.x;
+    const int lo = threadIdx.x * cell;
+    if (lo >= cnt) return;
+    const int len = min(cell, cnt - lo);
+    const long long slot = ((long long)(sec0 + sec) * cells_stride + ci);
+    double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v;
+    if (PASS == 1) {
+        s1 = state[slot * 4 + 0]; s2 = state[slot * 4 + 1]; h1 = state[slot * 4 + 2]; h2 = state[slot * 4 + 3];
+    }
+    const float* row = tile + threadIdx.x * ld;
+    double e = 0, e_prev = 0;
+    for (int t = 0; t < len; ++t) {
+        kw_step(K.cf, (double)row[t], s1, s2, h1, h2, v);
+        if (PASS == 1) { e_prev = e; e += v * v; }
+    }
+    if (PASS == 0) {
+        state[slot * 4 + 0] = s1; state[slot * 4 + 1] = s2; state[slot * 4 + 2] = h1; state[slot * 4 + 3] = h2;
+    } else {
+        energy[slot] = e;
+        if ((long long)ci * cell + len == n) energy_m1[sec0 + sec] = e_prev;
+    }
+}
+
+__device__ __forceinline__ void mat4_apply_add(const double* __restrict__ Mx, const double t[4], double s[4])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        s[r] += Mx[r * 4 + 0] * t[0] + Mx[r * 4 + 1] * t[1] + Mx[r * 4 + 2] * t[2] + Mx[r * 4 + 3] * t[3];
+}
+
+// One warp per section: turns zero-state end states into carry-in states, in place.
+__global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int sec0, int cells_stride,
+                          double* __restrict__ state)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nsec) return;
+    long long start;
+    int n;
+    section_bounds(G, warp, start, n);
+    const int ncells = (n + K.cell - 1) / K.cell;
+    double* st = state + (long long)(sec0 + warp) * cells_stride * 4;
+    double prev[4] = {0, 0, 0, 0};                           // state at the start of this group of 32 cells
+    for (int g0 = 0; g0 < ncells; g0 += 32) {
+        const int i = g0 + lane;
+        double s[4] = {0, 0, 0, 0};
+        if (i < ncells) { s[0] = st[i * 4]; s[1] = st[i * 4 + 1]; s[2] = st[i * 4 + 2]; s[3] = st[i * 4 + 3]; }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            double t[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) t[r] = __shfl_up_sync(0xffffffffu, s[r], 1 << k);
+            if (lane >= (1 << k)) mat4_apply_add(K.mpow + ((1 << k) - 1) * 16, t, s);
+        }
+        mat4_apply_add(K.mpow + lane * 16, prev, s);          // + Mc^(lane+1) * prev
+        double c[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            c[r] = __shfl_up_sync(0xffffffffu, s[r], 1);
+            if (lane == 0) c[r] = prev[r];
+        }
+        if (i < ncells) { st[i * 4] = c[0]; st[i * 4 + 1] = c[1]; st[i * 4 + 2] = c[2]; st[i * 4 + 3] = c[3]; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) prev[r] = __shfl_sync(0xffffffffu, s[r], 31);
+    }
+}
+
+// One warp per section: gating + gain.  lib.rs:142-214.
+__global__ void k_kw_gate(KwConfig K, SectionGeom G, int nsec, int sec0, int cells_stride,
+                          const double* __restrict__ energy, const double* __restrict__ energy_m1,
+                          double* __restrict__ lufs_out, double* __restrict__ gain_out, int out_stride)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nsec) return;
+    long long start;
+    int n;
+    section_bounds(G, warp, start, n);
+    const double* E = energy + (long long)(sec0 + warp) * cells_stride;
+    const int cell = K.cell;
+    const int ncells = (n + cell - 1) / cell;
+    const double rate = (double)K.rate;
+    const double NEG_INF = -INFINITY;
+    double lufs = NEG_INF;
+    if (n > 0) {
+        const double T = __ddiv_rn((double)n, rate);
+        if (T < 0.5) {
+            // block_size = T (apd.py:417): a single block [0, trunc(T*rate)) clipped to n
+            const double win = __dmul_rn(T, rate);
+            long long u = (long long)win;
+            if (u > n) u = n;
+            double tot = 0;
+            for (int i = lane; i < ncells; i += 32) tot += E[i];
+            tot = warp_sum(tot);
+            if (u == (long long)n - 1) {
+                // drop the last sample: replace the last cell's energy by the one without it
+                tot = 0;
+                for (int i = lane; i < ncells - 1; i += 32) tot += E[i];
+                tot = warp_sum(tot) + energy_m1[sec0 + warp];
+            }
+            // lib.rs:149-157 (num_blocks = round(0) + 1 = 1) then the two gates on one block
+            if (u > 0) {
+                const double ms = tot / (double)u;
+                if (ms > 0.0) {
+                    const double l = -0.691 + 10.0 * log10(ms);
+                    // abs gate, then relative gate = l - 10 < l: the block survives iff l >= -70
+                    if (l >= -70.0) lufs = -0.691 + 10.0 * log10(ms);
+                }
+            }
+        } else {
+            const double tg = 0.4;
+            const long long nb = llround(__ddiv_rn(__dsub_rn(T, tg), __dmul_rn(tg, 0.25))) + 1;   // lib.rs:149
+            const int hop = cell * K.k_per_hop, win = 4 * hop;
+            if (nb <= 0) {
+                double tot = 0;
+                for (int i = lane; i < ncells; i += 32) tot += E[i];
+                tot = warp_sum(tot);
+                const double ms = tot / (double)n;
+                lufs = ms <= 0.0 ? NEG_INF : -0.691 + 10.0 * log10(ms);
+            } else {
+                double gate = NEG_INF;
+                for (int pass = 0; pass < 2; ++pass) {
+                    double sum = 0;
+                    double cnt = 0;
+                    for (long long j = lane; j < nb; j += 32) {
+                        const long long l = j * hop;
+                        long long u = l + win;
+                        if (u > n) u = n;
+                        if (l >= u) continue;
+                        const int c0 = (int)(j * K.k_per_hop);
+                        const int c1 = min(c0 + 4 * K.k_per_hop, ncells);
+                        double e = 0;
+                        for (int c = c0; c < c1; ++c) e += E[c];
+                        const double ms = e / (double)(u - l);
+                        if (!(ms > 0.0)) continue;
+                        const double ld = -0.691 + 10.0 * log10(ms);
+                        const bool keep = pass == 0 ? (ld >= -70.0) : (ld > gate && ld >= -70.0);
+                        if (keep) { sum += ms; cnt += 1.0; }
+                    }
+                    sum = warp_sum(sum);
+                    cnt = warp_sum(cnt);
+                    if (cnt == 0.0) { lufs = NEG_INF; break; }
+                    const double mean = sum / cnt;
+                    if (pass == 0) gate = -0.691 + 10.0 * log10(mean) - 10.0;
+                    else lufs = -0.691 + 10.0 * log10(mean);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        lufs_out[(long long)warp * out_stride] = lufs;
+        gain_out[(long long)warp * out_stride] = pow(10.0, (kTargetLufs - lufs) / 20.0);   // lib.rs:221-222
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static void kw_coefficients(double rate, double cf[12])          // lib.rs:13-53
+{
+    const double A = pow(10.0, 4.0 / 40.0);
+    const double w = 2.0 * M_PI * (1500.0 / rate);
+    const double alpha = sin(w) / (2.0 * M_SQRT1_2);
+    const double c = cos(w);
+    const double k = 2.0 * sqrt(A) * alpha;
+    const double a0 = (A + 1.0) - (A - 1.0) * c + k;
+    cf[0] = A * ((A + 1.0) + (A - 1.0) * c + k) / a0;
+    cf[1] = -2.0 * A * ((A - 1.0) + (A + 1.0) * c) / a0;
+    cf[2] = A * ((A + 1.0) + (A - 1.0) * c - k) / a0;
+    cf[3] = 1.0;
+    cf[4] = 2.0 * ((A - 1.0) - (A + 1.0) * c) / a0;
+    cf[5] = ((A + 1.0) - (A - 1.0) * c - k) / a0;
+    const double w2 = 2.0 * M_PI * (38.0 / rate);
+    const double alpha2 = sin(w2) / (2.0 * 0.5);
+    const double c2 = cos(w2);
+    const double h0 = 1.0 + alpha2;
+    cf[6] = ((1.0 + c2) / 2.0) / h0;
+    cf[7] = (-(1.0 + c2)) / h0;
+    cf[8] = ((1.0 + c2) / 2.0) / h0;
+    cf[9] = 1.0;
+    cf[10] = (-2.0 * c2) / h0;
+    cf[11] = (1.0 - alpha2) / h0;
+}
+
+bool kw_config_create(int sample_rate, KwConfig* out, std::string* err)
+{
+    if (sample_rate <= 0 || sample_rate % 10 != 0) {
+        if (err) *err = "sample rate must be a positive multiple of 10 Hz (100 ms gating hop must be whole samples)";
+        return false;
+    }
+    KwConfig K;
+    memset(&K, 0, sizeof(K));
+    K.rate = sample_rate;
+    kw_coefficients((double)sample_rate, K.cf);
+    const int hop = sample_rate / 10;
+    int k = 1;
+    while (k <= hop && !(hop % k == 0 && hop / k <= 128)) ++k;
+    K.k_per_hop = k;
+    K.cell = hop / k;
+    // Mc = A^cell by running the zero-input response of the 4 unit states for `cell` samples
+    double Mc[16];
+    for (int col = 0; col < 4; ++col) {
+        double s[4] = {0, 0, 0, 0};
+        s[col] = 1.0;
+        for (int t = 0; t < K.cell; ++t) {
+            const double u = s[0];
+            const double n1 = -K.cf[4] * u + s[1];
+            const double n2 = -K.cf[5] * u;
+            const double v = K.cf[6] * u + s[2];
+            const double n3 = K.cf[7] * u - K.cf[10] * v + s[3];
+            const double n4 = K.cf[8] * u - K.cf[11] * v;
+            s[0] = n1; s[1] = n2; s[2] = n3; s[3] = n4;
+        }
+        for (int r = 0; r < 4; ++r) Mc[r * 4 + col] = s[r];
+    }
+    std::vector<double> pw(32 * 16);
+    memcpy(&pw[0], Mc, sizeof(Mc));
+    for (int p = 1; p < 32; ++p)
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double acc = 0;
+                for (int q = 0; q < 4; ++q) acc += pw[(p - 1) * 16 + r * 4 + q] * Mc[q * 4 + c];
+                pw[p * 16 + r * 4 + c] = acc;
+            }
+    double* d = nullptr;
+    if (cudaMalloc(&d, pw.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(d, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (err) *err = "cudaMalloc failed (loudness tables)";
+        return false;
+    }
+    K.mpow = d;
+    *out = K;
+    return true;
+}
+
+void kw_config_destroy(KwConfig* K)
+{
+    if (K->mpow) cudaFree((void*)K->mpow);
+    K->mpow = nullptr;
+}
+
+void launch_loudness(const KwConfig& K, const SectionGeom& G, int nsec, int sec0, int cells_stride,
+                     double* state, double* energy, double* energy_m1, double* lufs, double* gain,
+                     int out_stride, cudaStream_t st)
+{
+    if (nsec <= 0) return;
+    static bool attr = false;
+    const size_t smem = (size_t)128 * (K.cell + 1) * sizeof(float);
+    if (!attr) {
+        cudaFuncSetAttribute(k_kw_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(k_kw_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+    }
+    // the longest section of the launch decides the grid; CTAs past a section's end exit at once
+    long long start;
+    int nmax = 0;
+    for (int s = 0; s < nsec; ++s) {
+        int n;
+        section_bounds(G, s, start, n);
+        nmax = n > nmax ? n : nmax;
+    }
+    if (nmax <= 0) nmax = 1;
+    const int ncells = (nmax + K.cell - 1) / K.cell;
+    dim3 grid((ncells + 127) / 128, nsec);
+    const int wblocks = (nsec * 32 + 127) / 128;
+    k_kw_cells<0><<<grid, 128, smem, st>>>(K, G, sec0, cells_stride, state, energy, energy_m1);
+    k_kw_scan<<<wblocks, 128, 0, st>>>(K, G, nsec, sec0, cells_stride, state);
+    k_kw_cells<1><<<grid, 128, smem, st>>>(K, G, sec0, cells_stride, state, energy, energy_m1);
+    k_kw_gate<<<wblocks, 128, 0, st>>>(K, G, nsec, sec0, cells_stride, energy, energy_m1, lufs, gain, out_stride);
+}
+
+}  // namespace apd

@@ -1,0 +1,517 @@
+// Step 2: gather-and-verify kernels for the candidate peaks of the selected units.
+//
+//  * normal / short-clip verifier: reference audio_pattern_detector.py:622-623 (centred slice,
+//    renormalise), :773-804 (10-partition MSE), :808-846 + lib.rs:283-318, 651-675 (window-max
+//    down-sampling + Pearson r, decision on the centre window).
+//  * marker-tone verifier: reference audio_pattern_detector.py:642-750 and
+//    detection_utils.py:41-142 (Hann-windowed full-length spectrum and 25 ms STFT frames of the
+//    matched segment and both flanks, all float64).  The arbitrary-length DFT (L = 1223, 1827, ...)
+//    is evaluated exactly as a Bluestein chirp-z transform over a power-of-two float64 FFT.
+#include <cmath>
+
+#include "internal.h"
+#include "peaks.h"
+
+namespace apd {
+
+__device__ __forceinline__ double block_sum(double v, double* red)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+
+__device__ __forceinline__ float block_max(float v, double* red)
+{
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (double)v;
+    __syncthreads();
+    float t = 0.0f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t = fmaxf(t, (float)red[i]);
+    return t;
+}
+
+__device__ __forceinline__ void init_record(apd_candidate& r, int chunk, int clip, int peak, int kind, float h)
+{
+    r.chunk = chunk; r.clip = clip; r.peak = peak; r.flags = kind << APD_KIND_SHIFT;
+    r.height = h; r.similarity_whole = 0; r.similarity_middle = 0; r.reserved = 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < 3; ++i) r.pearson[i] = nan;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 5; ++j) r.tone[i][j] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// normal + short clip
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_verify_normal(VerifyArgs A)
+{
+    __shared__ double red[8];
+    __shared__ double part[10];
+    __shared__ float dsv[512];
+    const int slot = blockIdx.y;
+    if (A.pk.slot0 + slot >= *A.pk.sel_count) return;
+    const int2 unit = A.pk.sel[A.pk.slot0 + slot];
+    const int clip = unit.y;
+    if (A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0) return;
+    long long start;
+    int nsec;
+    section_bounds(A.pk.geom[A.pk.clip_group[clip]], unit.x, start, nsec);
+    const int L = A.pk.clip_len[clip];
+    const int n = nsec + L - 1;
+    const int W = 2 * L - 1;
+    const float* __restrict__ q = A.pk.corr + (long long)slot * A.pk.corr_stride;
+    const float* __restrict__ cc = A.cv.self_corr[clip];
+    const int np = A.pk.n_peaks[slot];
+    const int kind = A.cv.is_short[clip] ? 1 : 0;
+    for (int p = blockIdx.x; p < np; p += gridDim.x) {
+        const int pk = A.pk.peaks[(long long)slot * A.pk.peak_stride + p];
+        apd_candidate* rec = A.slot_cands + (long long)slot * A.pk.peak_stride + p;
+        const int half = W / 2;                                            // apd.py:534-535
+        if (pk + half > n + 5 || pk - half < -5) {                         // apd.py:541-546
+            if (threadIdx.x == 0) {
+                init_record(*rec, A.chunk0 + unit.x, clip, pk, kind, q[pk]);
+                rec->flags |= APD_FLAG_SKIPPED;
+            }
+            continue;
+        }
+        const int beg = pk - (L - 1);                                      // au.py:177-191
+        // max of the zero-padded slice
+        float m = 0.0f;
+        for (int t = threadIdx.x; t < W; t += blockDim.x) {
+            const int k = beg + t;
+            if (k >= 0 && k < n) m = fmaxf(m, q[k]);
+        }
+        const float smax = block_max(m, red);
+        // partition MSEs (float32 element ops as numpy, float64 accumulation)
+        const int ps = W / 10;
+        double acc[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+        for (int t = threadIdx.x; t < ps * 10; t += blockDim.x) {
+            const int k = beg + t;
+            const float s = (k >= 0 && k < n) ? q[k] / smax : 0.0f / smax;
+            const float d = cc[t] - s;
+            const float d2 = d * d;
+            const int i = t / ps;
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+                if (j == i) acc[j] += (double)d2;
+        }
+        for (int i = 0; i < 10; ++i) {
+            const double s = block_sum(acc[i], red);
+            if (threadIdx.x == 0) part[i] = s;
+        }
+        __syncthreads();
+        float parts[10];
+        float whole = 0.0f;
+        for (int i = 0; i < 10; ++i) {
+            parts[i] = (float)(part[i] / (double)ps);
+            whole += parts[i];
+        }
+        whole = whole / 10.0f;                                             // apd.py:786
+        const float middle = (parts[4] + parts[5]) / 2.0f;                 // apd.py:785
+        const float sim = kind ? whole : fminf(whole, middle);             // apd.py:788-791
+        double r[3] = {__longlong_as_double(0x7ff8000000000000LL), __longlong_as_double(0x7ff8000000000000LL),
+                       __longlong_as_double(0x7ff8000000000000LL)};
+        bool accept = false;
+        if (!(sim > kMseLimit)) {                                          // apd.py:796
+            const float* __restrict__ cache = A.cv.win_cache[clip];
+            int cache_off = 0;
+            for (int w = 0; w < 3; ++w) {
+                const int ds = A.cv.win_ds[clip * 3 + w];
+                if (ds <= 0) continue;
+                const int lo = A.cv.win_lo[clip * 3 + w], hi = A.cv.win_hi[clip * 3 + w];
+                const int nw = hi - lo;
+                const double step = (double)nw / (double)ds;               // lib.rs:289
+                __syncthreads();
+                for (int i = threadIdx.x; i < ds; i += blockDim.x) {
+                    int a = (int)((double)i * step);
+                    int b = (int)((double)(i + 1) * step);
+                    if (b <= a) b = a + 1;
+                    if (a >= nw) a = nw - 1;
+                    if (b > nw) b = nw;
+                    float mx = -INFINITY;
+                    for (int t = a; t < b; ++t) {
+                        const int k = beg + lo + t;
+                        const float s = (k >= 0 && k < n) ? q[k] : 0.0f;
+                        mx = fmaxf(mx, s);
+                    }
+                    dsv[i] = mx / smax;
+                }
+                __syncthreads();
+                double sx = 0, sy = 0;
+                for (int i = threadIdx.x; i < ds; i += blockDim.x) { sx += (double)cache[cache_off + i]; sy += (double)dsv[i]; }
+                const double mx_ = block_sum(sx, red) / (double)ds;
+                const double my_ = block_sum(sy, red) / (double)ds;
+                double cov = 0, vx = 0, vy = 0;
+                for (int i = threadIdx.x; i < ds; i += blockDim.x) {
+                    const double dx = (double)cache[cache_off + i] - mx_, dy = (double)dsv[i] - my_;
+                    cov += dx * dy; vx += dx * dx; vy += dy * dy;
+                }
+                cov = block_sum(cov, red);
+                vx = block_sum(vx, red);
+                vy = block_sum(vy, red);
+                const double den = sqrt(vx * vy);
+                r[w] = den == 0.0 ? 0.0 : cov / den;                       // lib.rs:670-674
+                cache_off += ds;
+            }
+            const int center = kind ? 0 : 1;                               // apd.py:813,820
+            accept = r[center] >= kPearsonMin;                             // apd.py:897
+        }
+        if (threadIdx.x == 0) {
+            init_record(*rec, A.chunk0 + unit.x, clip, pk, kind, q[pk]);
+            rec->similarity_whole = whole;
+            rec->similarity_middle = middle;
+            for (int w = 0; w < 3; ++w) rec->pearson[w] = r[w];
+            if (accept) rec->flags |= APD_FLAG_ACCEPT;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// marker tone
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 zmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// In-place-semantics float64 FFT of length P (power of two) by one CTA, Stockham radix-2,
+// ping-ponging between x and y in global memory; returns the buffer holding the result.
+// tw[t] = e^{-2 pi i t / P}, t < P/2.  INV conjugates the twiddles (unnormalised inverse).
+template <bool INV>
+__device__ double2* fft64(double2* x, double2* y, const double2* __restrict__ tw, int P)
+{
+    const int half = P >> 1;
+    int lg = 0;
+    for (int Ns = 1; Ns < P; Ns <<= 1, ++lg) {
+        const int tstep = half / Ns;
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            const int k = j & (Ns - 1);
+            double2 w = tw[k * tstep];
+            if (INV) w.y = -w.y;
+            const double2 a = x[j];
+            const double2 b = zmul(x[j + half], w);
+            const int o = ((j >> lg) << (lg + 1)) + k;
+            y[o] = make_double2(a.x + b.x, a.y + b.y);
+            y[o + Ns] = make_double2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+        double2* t = x; x = y; y = t;
+    }
+    return x;
+}
+
+__device__ __forceinline__ double2 chirp(long long n, int L, double sign)   // e^{sign * i pi n^2 / L}
+{
+    const long long r = (n * n) % (2LL * L);
+    double s, c;
+    sincospi(sign * (double)r / (double)L, &s, &c);
+    return make_double2(c, s);
+}
+
+// Builds FFT_P of the wrapped chirp b[m] = e^{+i pi m^2 / L} (|m| < L) for one tone clip (init time).
+__global__ void __launch_bounds__(1024)
+k_tone_chirp_fft(int L, int P, const double2* __restrict__ tw, double2* buf0, double2* buf1, double2* out)
+{
+    for (int m = threadIdx.x; m < P; m += blockDim.x) {
+        double2 v = make_double2(0, 0);
+        if (m < L) v = chirp(m, L, +1.0);
+        else if (P - m < L) v = chirp(P - m, L, +1.0);
+        buf0[m] = v;
+    }
+    __syncthreads();
+    const double2* r = fft64<false>(buf0, buf1, tw, P);
+    for (int m = threadIdx.x; m < P; m += blockDim.x) out[m] = r[m];
+}
+
+struct ToneItem { int slot; int p; };
+
+__global__ void k_tone_worklist(VerifyArgs A, int nslots, ToneItem* items, int* n_items, int capacity)
+{
+    // one thread: ordered list of (slot, peak) pairs of tone clips (few entries)
+    if (blockIdx.x || threadIdx.x) return;
+    int cnt = 0;
+    for (int s = 0; s < nslots; ++s) {
+        if (A.pk.slot0 + s >= *A.pk.sel_count) break;
+        const int clip = A.pk.sel[A.pk.slot0 + s].y;
+        if (!(A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0)) continue;
+        for (int p = 0; p < A.pk.n_peaks[s]; ++p) {
+            if (cnt < capacity) items[cnt] = ToneItem{s, p};
+            ++cnt;
+        }
+    }
+    *n_items = cnt < capacity ? cnt : capacity;
+    if (cnt > capacity) atomicOr(A.pk.overflow, 2);
+}
+
+// metrics[item][seg][5]
+__global__ void __launch_bounds__(1024)
+k_tone_metrics(VerifyArgs A, const ToneItem* __restrict__ items, const int* __restrict__ n_items,
+               double* __restrict__ metrics)
+{
+    extern __shared__ double2 ftw[];            // frame twiddles e^{-2 pi i t / wl}, then frame Hann (as .x)
+    __shared__ double red[32];
+    __shared__ int s_arg;
+    const int seg = blockIdx.x;                 // 0 match, 1 left flank, 2 right flank
+    double2* buf0 = A.tone_scratch + ((long long)blockIdx.y * 3 + seg) * 2 * A.tone_scratch_stride;
+    double2* buf1 = buf0 + A.tone_scratch_stride;
+    const int sr = A.sample_rate;
+    double wlr = rint(0.025 * (double)sr);                                   // du.py:77 (banker's round)
+    const int wl = wlr > 32.0 ? (int)wlr : 32;
+    const int hop = wl / 2 > 1 ? wl / 2 : 1;
+    for (int t = threadIdx.x; t < wl; t += blockDim.x) {
+        double s, c;
+        sincospi(-2.0 * (double)t / (double)wl, &s, &c);
+        ftw[t] = make_double2(c, s);
+        const double h = wl > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(wl - 1)) : 1.0;
+        ftw[wl + t] = make_double2(h, 0.0);
+    }
+    __syncthreads();
+    for (int it = blockIdx.y; it < *n_items; it += gridDim.y) {
+        const int slot = items[it].slot, p = items[it].p;
+        const int2 unit = A.pk.sel[A.pk.slot0 + slot];
+        const int clip = unit.y;
+        const int g = A.pk.clip_group[clip];
+        long long start;
+        int nsec;
+        section_bounds(A.pk.geom[g], unit.x, start, nsec);
+        const float* __restrict__ x = A.pk.geom[g].audio + (start - A.pk.geom[g].base);
+        const double gain = A.gains[(long long)unit.x * A.n_groups + g];
+        const int L = A.pk.clip_len[clip];
+        const int P = A.cv.tone_P[clip];
+        const double2* __restrict__ tw = A.cv.tone_tw[clip];
+        const double2* __restrict__ cf = A.cv.tone_chirp_fft[clip];
+        const double f0 = A.cv.tone_hz[clip];
+        const int pk = A.pk.peaks[(long long)slot * A.pk.peak_stride + p];
+        const int ms = pk - L + 1 + (seg == 1 ? -L : (seg == 2 ? L : 0));    // apd.py:650-653
+        double* out = metrics + ((long long)it * 3 + seg) * 5;
+        const double band = fmax(40.0, f0 * 0.08), lock = fmax(20.0, f0 * 0.04);   // du.py:56-57
+        const double d = __ddiv_rn(1.0, (double)sr);
+        const double fval = __ddiv_rn(1.0, __dmul_rn((double)L, d));         // np.fft.rfftfreq
+        const double fvalw = __ddiv_rn(1.0, __dmul_rn((double)wl, d));
+
+        // ---- full-length Hann-windowed spectrum via Bluestein
+        for (int n = threadIdx.x; n < P; n += blockDim.x) {
+            double2 v = make_double2(0, 0);
+            if (n < L) {
+                const int k = ms + n;
+                const double xv = (k >= 0 && k < nsec) ? (double)normalize_sample(x[k], gain) : 0.0;
+                const double h = L > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)n / (double)(L - 1)) : 1.0;
+                const double2 c = chirp(n, L, -1.0);
+                v = make_double2(xv * h * c.x, xv * h * c.y);
+            }
+            buf0[n] = v;
+        }
+        __syncthreads();
+        double2* r = fft64<false>(buf0, buf1, tw, P);
+        double2* o = r == buf0 ? buf1 : buf0;
+        for (int n = threadIdx.x; n < P; n += blockDim.x) r[n] = zmul(r[n], cf[n]);
+        __syncthreads();
+        double2* c = fft64<true>(r, o, tw, P);
+        const int nb = L / 2 + 1;
+        const double invP = 1.0 / (double)P;
+        double tot = 0, bsum = 0, best = -1.0;
+        int arg = 0x7fffffff;
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+            const double2 z = zmul(c[k], chirp(k, L, -1.0));
+            const double re = z.x * invP, im = z.y * invP;
+            const double m2 = re * re + im * im;
+            tot += m2;
+            if (fabs(__dmul_rn((double)k, fval) - f0) <= band) bsum += m2;    // du.py:74
+            if (m2 > best) { best = m2; arg = k; }
+        }
+        tot = block_sum(tot, red);
+        bsum = block_sum(bsum, red);
+        // argmax, first maximum wins (np.argmax)
+        {
+            double bm = best;
+            for (int o2 = 16; o2 > 0; o2 >>= 1) bm = fmax(bm, __shfl_xor_sync(0xffffffffu, bm, o2));
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bm;
+            if (threadIdx.x == 0) s_arg = 0x7fffffff;
+            __syncthreads();
+            double gm = -1.0;
+            for (int i = 0; i < (blockDim.x >> 5); ++i) gm = fmax(gm, red[i]);
+            if (best == gm && arg != 0x7fffffff) atomicMin(&s_arg, arg);
+            __syncthreads();
+        }
+        const int argk = s_arg == 0x7fffffff ? 0 : s_arg;
+        const double detected = __dmul_rn((double)argk, fval);               // du.py:62
+
+        // ---- STFT frames (du.py:77-112): direct DFT of each Hann-windowed frame
+        const int nf = L - wl > 0 ? (L - wl + hop - 1) / hop : 0;             // range(0, L - wl, hop)
+        const int nbw = wl / 2 + 1;
+        __syncthreads();                                                      // conv buffer no longer needed
+        double* fm2 = (double*)buf0;                                          // [frame][bin] |X|^2
+        if (tot != 0.0) {
+            for (long long w = threadIdx.x; w < (long long)nf * nbw; w += blockDim.x) {
+                const int f = (int)(w / nbw), kb = (int)(w % nbw);
+                const int s0 = ms + f * hop;
+                double re = 0, im = 0;
+                int ph = 0;
+                for (int n = 0; n < wl; ++n) {
+                    const int k = s0 + n;
+                    const double xv = (k >= 0 && k < nsec) ? (double)normalize_sample(x[k], gain) : 0.0;
+                    const double xw = xv * ftw[wl + n].x;
+                    const double2 e = ftw[ph];
+                    re += xw * e.x;
+                    im += xw * e.y;
+                    ph += kb;
+                    if (ph >= wl) ph -= wl;
+                }
+                fm2[w] = re * re + im * im;
+            }
+        }
+        __syncthreads();
+        // per-frame reductions by single threads, then the run-length logic by thread 0
+        double* fpur = (double*)buf1;              // [frame] purity (or -1 = zero-energy frame)
+        unsigned char* fact = (unsigned char*)(fpur + nf);
+        if (tot != 0.0) {
+            for (int f = threadIdx.x; f < nf; f += blockDim.x) {
+                double e = 0, bs = 0, bm = -1.0;
+                int ak = 0;
+                for (int kb = 0; kb < nbw; ++kb) {
+                    const double m2 = fm2[(long long)f * nbw + kb];
+                    e += m2;
+                    if (fabs(__dmul_rn((double)kb, fvalw) - f0) <= band) bs += m2;
+                    if (m2 > bm) { bm = m2; ak = kb; }
+                }
+                if (e == 0.0) { fpur[f] = -1.0; fact[f] = 0; continue; }
+                const double fdom = __dmul_rn((double)ak, fvalw);
+                const double pur = bs / e;
+                const double tol = fmax(1e-9 * fmax(fabs(fdom), fabs(f0)), lock);    // math.isclose
+                fpur[f] = pur;
+                fact[f] = (fabs(fdom - f0) <= tol && pur >= 0.55) ? 1 : 0;           // du.py:102-105
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ratio = 0, meanp = 0;
+            int longest = 0;
+            if (tot != 0.0) {
+                int frames = 0, active = 0, run = 0;
+                double psum = 0;
+                for (int f = 0; f < nf; ++f) {
+                    if (fpur[f] < 0.0) { run = 0; continue; }
+                    ++frames;
+                    if (fact[f]) { ++active; ++run; longest = run > longest ? run : longest; psum += fpur[f]; }
+                    else run = 0;
+                }
+                ratio = frames > 0 ? (double)active / (double)frames : 0.0;
+                meanp = active > 0 ? psum / (double)active : 0.0;
+            }
+            out[0] = detected;
+            out[1] = tot != 0.0 ? bsum / tot : 0.0;                           // du.py:64-75
+            out[2] = ratio;
+            out[3] = (double)longest;
+            out[4] = meanp;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_tone_decide(VerifyArgs A, const ToneItem* __restrict__ items, const int* __restrict__ n_items,
+                              const double* __restrict__ metrics)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= *n_items) return;
+    const int slot = items[it].slot, p = items[it].p;
+    const int2 unit = A.pk.sel[A.pk.slot0 + slot];
+    const int clip = unit.y;
+    const int pk = A.pk.peaks[(long long)slot * A.pk.peak_stride + p];
+    long long start;
+    int nsec;
+    section_bounds(A.pk.geom[A.pk.clip_group[clip]], unit.x, start, nsec);
+    const int L = A.pk.clip_len[clip];
+    const int n = nsec + L - 1, half = (2 * L - 1) / 2;
+    apd_candidate* rec = A.slot_cands + (long long)slot * A.pk.peak_stride + p;
+    const float h = A.pk.corr[(long long)slot * A.pk.corr_stride + pk];
+    init_record(*rec, A.chunk0 + unit.x, clip, pk, 2, h);
+    if (pk + half > n + 5 || pk - half < -5) { rec->flags |= APD_FLAG_SKIPPED; return; }
+    const double* m = metrics + (long long)it * 15;
+    for (int s = 0; s < 3; ++s) for (int j = 0; j < 5; ++j) rec->tone[s][j] = m[s * 5 + j];
+    const double* th = A.cv.tone_thr + clip * 6;
+    const double f0 = A.cv.tone_hz[clip];
+    const double lo = fmin(m[5 + 1], m[10 + 1]), hi = fmax(m[5 + 1], m[10 + 1]);
+    bool ok = fabs(m[0] - f0) <= fmax(0.05 * fmax(fabs(m[0]), fabs(f0)), 0.0);   // apd.py:707
+    ok = ok && m[1] >= th[0] && m[2] >= th[1] && (long long)m[3] >= (long long)th[2] && m[4] >= th[3]
+            && lo <= th[4] && hi <= th[5];                                         // apd.py:717-724
+    if (ok) rec->flags |= APD_FLAG_ACCEPT;
+}
+
+// Ordered gather of the per-slot records into the output list.
+__global__ void __launch_bounds__(256)
+k_emit(VerifyArgs A, int nslots)
+{
+    __shared__ int s_off[1025];
+    if (threadIdx.x == 0) {
+        int off = *A.out_count;
+        for (int s = 0; s < nslots; ++s) {
+            s_off[s] = off;
+            if (A.pk.slot0 + s < *A.pk.sel_count) off += A.pk.n_peaks[s];
+        }
+        s_off[nslots] = off;
+    }
+    __syncthreads();
+    for (int s = 0; s < nslots; ++s) {
+        if (A.pk.slot0 + s >= *A.pk.sel_count) break;
+        const int np = A.pk.n_peaks[s];
+        for (int p = threadIdx.x; p < np; p += blockDim.x) {
+            const int o = s_off[s] + p;
+            if (o < A.out_capacity) A.out[o] = A.slot_cands[(long long)s * A.pk.peak_stride + p];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_off[nslots] > A.out_capacity) atomicOr(A.pk.overflow, 4);
+        *A.out_count = s_off[nslots] < A.out_capacity ? s_off[nslots] : A.out_capacity;
+    }
+}
+
+void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
+{
+    if (nslots <= 0) return;
+    dim3 gn(8, nslots);
+    k_verify_normal<<<gn, 256, 0, st>>>(A);
+    ++*launches;
+}
+
+void launch_tone(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
+                 double* metrics, int tone_ctas, int wl, cudaStream_t st, long long* launches)
+{
+    if (nslots <= 0 || tone_ctas <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_tone_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+    }
+    k_tone_worklist<<<1, 32, 0, st>>>(A, nslots, (ToneItem*)items, n_items, item_capacity);
+    dim3 g(3, tone_ctas);
+    k_tone_metrics<<<g, 1024, (size_t)2 * wl * sizeof(double2), st>>>(A, (const ToneItem*)items, n_items, metrics);
+    k_tone_decide<<<(item_capacity + 127) / 128, 128, 0, st>>>(A, (const ToneItem*)items, n_items, metrics);
+    *launches += 3;
+}
+
+void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
+{
+    if (nslots <= 0) return;
+    k_emit<<<1, 256, 0, st>>>(A, nslots);
+    ++*launches;
+}
+
+size_t tone_item_bytes() { return sizeof(ToneItem); }
+
+void launch_chirp_fft(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* out, cudaStream_t st)
+{
+    k_tone_chirp_fft<<<1, 1024, 0, st>>>(L, P, tw, buf0, buf1, out);
+}
+
+}  // namespace apd
