@@ -225,6 +225,22 @@ class AudioPatternDetector:
         return {"sliding_window": sw.value, "lufs": lufs.value, "self_max": smax.value, "fft_points": nfft.value,
                 "normalized": norm, "self_correlation": cc}
 
+    def enable_profiling(self, on: bool = True) -> None:
+        _lib.check(_lib.lib().apd_profile(self._ctx, 1 if on else 0), "apd_profile")
+
+    def stage_times_ms(self, reset: bool = True) -> dict[str, float]:
+        ms = (C.c_double * 4)()
+        _lib.check(_lib.lib().apd_profile_read(self._ctx, ms, 1 if reset else 0), "apd_profile_read")
+        return dict(zip(("loudness", "forward_fft", "correlate_max", "peaks_verify"), ms))
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().apd_launch_count(self._ctx))
+
+    def unit_n_out(self, chunk: int, clip_index: int, total_samples: int) -> int:
+        n = C.c_int32()
+        _lib.check(_lib.lib().apd_unit_n_out(self._ctx, chunk, clip_index, total_samples, C.byref(n)), "unit_n_out")
+        return n.value
+
     # ------------------------------------------------------------------ timestamps
     def _timestamp(self, peak: int, chunk: int, clip_index: int) -> float:
         """reference :585 then :440-451, same order of float operations."""
@@ -301,8 +317,8 @@ class AudioPatternDetector:
         torch = _torch()
         if isinstance(audio, np.ndarray):
             dev = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(f"cuda:{self._device}")
-        else:
-            dev = audio.to(device=f"cuda:{self._device}", dtype=torch.float32).contiguous()
+        else:   # torch tensor: CUDA (used in place) or host (pinned host memory copies at full PCIe rate)
+            dev = audio.to(device=f"cuda:{self._device}", dtype=torch.float32, non_blocking=True).contiguous()
         n = dev.numel()
         C_ = self._chunk_samples
         n_chunks = (n + C_ - 1) // C_

@@ -45,6 +45,8 @@ struct ClipHost {
     int tone_P = 0;
     double2* d_tone_chirp = nullptr;
     double2* d_tone_tw = nullptr;
+    double2* d_tone_pre = nullptr;
+    double2* d_tone_post = nullptr;
 };
 
 struct Group {
@@ -173,6 +175,8 @@ struct apd_ctx {
     double *d_tone_hz = nullptr, *d_tone_thr = nullptr;
     const double2** d_tone_chirp_ptrs = nullptr;
     const double2** d_tone_tw_ptrs = nullptr;
+    const double2** d_tone_pre_ptrs = nullptr;
+    const double2** d_tone_post_ptrs = nullptr;
     SectionGeom* d_geoms = nullptr;
     SectionGeom* h_geoms = nullptr;       // pinned
 
@@ -196,6 +200,7 @@ struct apd_ctx {
     float* d_cand_val = nullptr;
     unsigned char* d_cand_state = nullptr;
     int* d_peaks = nullptr;
+    float* d_peak_height = nullptr;
     int *d_n_peaks = nullptr, *d_n_cands = nullptr;
     apd_candidate* d_slot_cands = nullptr;
     apd_candidate* d_out = nullptr;
@@ -206,6 +211,11 @@ struct apd_ctx {
     double2* d_tone_scratch = nullptr;
     void* d_tone_items = nullptr;
     double* d_tone_metrics = nullptr;
+
+    // optional stage timing (CUDA events on the caller's stream)
+    bool profile = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double stage_ms[4] = {0, 0, 0, 0};
 
     // state of the staged batch
     const float* audio = nullptr;
@@ -388,7 +398,8 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     std::vector<const float*> h_cc(n_clips), h_cache(n_clips);
     std::vector<const float2*> h_spec(n_clips);
     std::vector<double> h_thz(n_clips), h_thr(n_clips * 6);
-    std::vector<const double2*> h_chirp(n_clips, nullptr), h_tw(n_clips, nullptr);
+    std::vector<const double2*> h_chirp(n_clips, nullptr), h_tw(n_clips, nullptr), h_pre(n_clips, nullptr),
+        h_post(n_clips, nullptr);
     int max_P = 0;
     for (int p = 0; p < n_clips; ++p) {
         ClipHost& cl = c->clips[p];
@@ -438,15 +449,18 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
             }
             CK(upload(&cl.d_tone_tw, tw));
             CK(dalloc(&cl.d_tone_chirp, (size_t)P));
+            CK(dalloc(&cl.d_tone_pre, (size_t)L));
+            CK(dalloc(&cl.d_tone_post, (size_t)L / 2 + 1));
             double2 *b0 = nullptr, *b1 = nullptr;
             CK(dalloc(&b0, (size_t)P));
             CK(dalloc(&b1, (size_t)P));
-            launch_chirp_fft(L, P, cl.d_tone_tw, b0, b1, cl.d_tone_chirp, 0);
+            launch_tone_tables(L, P, cl.d_tone_tw, b0, b1, cl.d_tone_chirp, cl.d_tone_pre, cl.d_tone_post, 0);
             CK(cudaDeviceSynchronize());
             cudaFree(b0);
             cudaFree(b1);
             ++c->launches;
             h_P[p] = P; h_chirp[p] = cl.d_tone_chirp; h_tw[p] = cl.d_tone_tw;
+            h_pre[p] = cl.d_tone_pre; h_post[p] = cl.d_tone_post;
         }
     }
     CK(cudaDeviceSynchronize());
@@ -466,6 +480,8 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(upload(&c->d_tone_thr, h_thr));
     CK(upload(&c->d_tone_chirp_ptrs, h_chirp));
     CK(upload(&c->d_tone_tw_ptrs, h_tw));
+    CK(upload(&c->d_tone_pre_ptrs, h_pre));
+    CK(upload(&c->d_tone_post_ptrs, h_post));
     cudaFree(d_tmp_max); cudaFree(d_tmp_int); cudaFree(d_zero_f); cudaFree((void*)d_tmp_ptr);
     cudaFree(d_tl); cudaFree(d_tg); cudaFree(d_tstate); cudaFree(d_ten); cudaFree(d_tem1);
 
@@ -498,6 +514,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(dalloc(&c->d_cand_val, (size_t)c->n_slots * c->cand_stride));
     CK(dalloc(&c->d_cand_state, (size_t)c->n_slots * c->cand_stride));
     CK(dalloc(&c->d_peaks, (size_t)c->n_slots * c->peak_stride));
+    CK(dalloc(&c->d_peak_height, (size_t)c->n_slots * c->peak_stride));
     CK(dalloc(&c->d_n_peaks, (size_t)c->n_slots));
     CK(dalloc(&c->d_n_cands, (size_t)c->n_slots));
     CK(dalloc(&c->d_slot_cands, (size_t)c->n_slots * c->peak_stride));
@@ -508,7 +525,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         const long long per_cta = 3LL * 2 * max_P * (long long)sizeof(double2);
         c->tone_ctas = (int)std::max<long long>(1, std::min<long long>(64, (1LL << 31) / per_cta));
         CK(dalloc(&c->d_tone_scratch, (size_t)c->tone_ctas * 3 * 2 * max_P));
-        c->tone_item_cap = c->n_slots * 16;
+        c->tone_item_cap = std::max(4096, B * n_clips);
         CK(cudaMalloc(&c->d_tone_items, tone_item_bytes() * c->tone_item_cap));
         CK(dalloc(&c->d_tone_metrics, (size_t)c->tone_item_cap * 15));
         const double wlr = std::nearbyint(0.025 * (double)sample_rate);
@@ -527,6 +544,7 @@ extern "C" int apd_destroy(apd_ctx* c)
     for (auto& cl : c->clips) {
         cudaFree(cl.d_raw); cudaFree(cl.d_norm); cudaFree(cl.d_rev); cudaFree(cl.d_spec);
         cudaFree(cl.d_self_corr); cudaFree(cl.d_win_cache); cudaFree(cl.d_tone_chirp); cudaFree(cl.d_tone_tw);
+        cudaFree(cl.d_tone_pre); cudaFree(cl.d_tone_post);
     }
     for (auto& g : c->groups) { free_plan(&g.plan); cudaFree(g.d_clips); cudaFree(g.d_sel); }
     for (auto& kv : c->self_plans) free_plan(&kv.second);
@@ -534,13 +552,16 @@ extern "C" int apd_destroy(apd_ctx* c)
     void* ptrs[] = {c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
                     c->d_win_ds, c->d_tone_P, c->d_self_max, (void*)c->d_self_corr_ptrs, (void*)c->d_win_cache_ptrs,
                     (void*)c->d_clip_spec_ptrs, c->d_tone_hz, c->d_tone_thr, (void*)c->d_tone_chirp_ptrs,
-                    (void*)c->d_tone_tw_ptrs, c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
+                    (void*)c->d_tone_tw_ptrs, (void*)c->d_tone_pre_ptrs, (void*)c->d_tone_post_ptrs, c->d_peak_height,
+                    c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
                     c->d_gain, c->d_spec, c->d_scratch, c->d_unit_max, c->d_unit_npeaks, c->d_counts, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
                     c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(c->h_geoms);
     cudaFreeHost(c->h_counts);
+    for (int i = 0; i < 5; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
     return APD_OK;
 }
@@ -653,6 +674,8 @@ static int stage_peaks_verify(apd_ctx* c, cudaStream_t st)
     }
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    bool any_tone = false;
+    VerifyArgs last_va{};
     for (int g = 0; g < G; ++g) {
         Group& gr = c->groups[g];
         const int cnt = c->h_counts[g];
@@ -665,27 +688,34 @@ static int stage_peaks_verify(apd_ctx* c, cudaStream_t st)
             c->launches += 2;
             PeakArgs PA{gr.d_sel, c->d_counts + g, u0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
                         c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
-                        c->d_peaks, c->peak_stride, c->d_n_peaks, c->d_n_cands, c->d_counts + G + 1};
+                        c->d_peaks, c->d_peak_height, c->peak_stride, c->d_n_peaks, c->d_n_cands,
+                        c->d_counts + G + 1};
             launch_find_peaks(PA, ns, st);
             ++c->launches;
             ClipVerify CV{c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_self_corr_ptrs, c->d_win_lo,
                           c->d_win_hi, c->d_win_ds, c->d_win_cache_ptrs, c->d_is_short, c->d_tone_hz, c->d_tone_thr,
-                          c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs};
+                          c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs, c->d_tone_pre_ptrs,
+                          c->d_tone_post_ptrs};
             VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + G, c->out_capacity,
                           c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
             launch_verify(VA, ns, st, &c->launches);
             bool group_has_tone = false;
             for (int p : gr.clips)
                 group_has_tone |= c->clips[p].strategy == APD_STRATEGY_MARKER_TONE && c->clips[p].tone_hz > 0.0;
-            if (group_has_tone)
-                launch_tone(VA, ns, c->d_tone_items, c->d_counts + G + 2, c->tone_item_cap, c->d_tone_metrics,
-                            c->tone_ctas, c->tone_wl, st, &c->launches);
+            if (group_has_tone) {
+                launch_tone_collect(VA, ns, c->d_tone_items, c->d_counts + G + 2, c->tone_item_cap, st, &c->launches);
+                any_tone = true;
+            }
+            last_va = VA;
             launch_emit(VA, ns, st, &c->launches);
             k_record_npeaks<<<(ns + 127) / 128, 128, 0, st>>>(gr.d_sel, c->d_counts + g, u0, ns, c->d_n_peaks,
                                                              c->n_clips, c->d_unit_npeaks);
             ++c->launches;
         }
     }
+    if (any_tone)     // all tone candidates of the batch in one launch (they only read raw audio + gains)
+        launch_tone_batch(last_va, c->d_tone_items, c->d_counts + G + 2, c->tone_item_cap, c->d_tone_metrics,
+                          c->tone_ctas, c->tone_wl, st, &c->launches);
     CK(cudaGetLastError());
     return APD_OK;
 }
@@ -779,11 +809,24 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
     if (!cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null output");
     int rc = stage_begin(c, audio, base, n, cb, ce, st);
     if (rc) return rc;
+    const bool prof = c->profile;
+    if (prof) cudaEventRecord(c->ev[0], st);
     if ((rc = stage_loudness(c, st))) return rc;
+    if (prof) cudaEventRecord(c->ev[1], st);
     if ((rc = stage_forward(c, st))) return rc;
+    if (prof) cudaEventRecord(c->ev[2], st);
     if ((rc = stage_correlate_max(c, st))) return rc;
+    if (prof) cudaEventRecord(c->ev[3], st);
     if ((rc = stage_peaks_verify(c, st))) return rc;
-    return collect(c, cand_host, cap, n_cand, trace, lufs_host, st);
+    if (prof) cudaEventRecord(c->ev[4], st);
+    rc = collect(c, cand_host, cap, n_cand, trace, lufs_host, st);
+    if (prof && rc == APD_OK) {
+        for (int i = 0; i < 4; ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->stage_ms[i] += ms;
+        }
+    }
+    return rc;
 }
 
 extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t clip, float* out_host, int32_t capacity,
@@ -816,6 +859,26 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
 }
 
 extern "C" int64_t apd_launch_count(apd_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int apd_profile(apd_ctx* c, int enable)
+{
+    if (!c) return fail(APD_ERR_INVALID, "apd_profile: null context");
+    CK(cudaSetDevice(c->device));
+    if (enable && !c->ev[0])
+        for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&c->ev[i]));
+    c->profile = enable != 0;
+    return APD_OK;
+}
+
+extern "C" int apd_profile_read(apd_ctx* c, double* ms4, int reset)
+{
+    if (!c || !ms4) return fail(APD_ERR_INVALID, "apd_profile_read: bad arguments");
+    for (int i = 0; i < 4; ++i) {
+        ms4[i] = c->stage_ms[i];
+        if (reset) c->stage_ms[i] = 0.0;
+    }
+    return APD_OK;
+}
 
 extern "C" int apd_unit_n_out(apd_ctx* c, int32_t chunk, int32_t clip, int64_t total_samples, int32_t* n_out)
 {

@@ -22,14 +22,13 @@ struct PeakArgs {
     unsigned char* cand_state;
     long long cand_stride;
     int* peaks;                   // per slot result, capacity peak_stride
+    float* peak_height;           // normalised correlation at each surviving peak
     int peak_stride;
     int* n_peaks;                 // per slot
     int* n_cands;                 // per slot (local maxima >= height before the distance filter)
     int* overflow;
 };
 
-void launch_select(const unsigned int* unit_max_bits, const float* self_max, int n_clips, int n_units,
-                   float height, int2* sel, int* sel_count, int capacity, cudaStream_t st);
 void launch_find_peaks(const PeakArgs& A, int nslots, cudaStream_t st);
 
 // Per-clip verification data (device arrays indexed by clip).
@@ -49,6 +48,8 @@ struct ClipVerify {
     const int* tone_P;                // Bluestein FFT length (power of two >= 2L-1)
     const double2* const* tone_chirp_fft;   // [clip] -> FFT_P of the chirp
     const double2* const* tone_tw;          // [clip] -> e^{-2 pi i t / P}, t < P/2
+    const double2* const* tone_pre;         // [clip] -> hann[n] * e^{-i pi n^2 / L}, n < L
+    const double2* const* tone_post;        // [clip] -> e^{-i pi k^2 / L}, k <= L/2
 };
 
 struct VerifyArgs {
@@ -70,10 +71,13 @@ struct VerifyArgs {
 constexpr int kMaxSlots = 1024;           // slots per phase-2 round (k_emit keeps offsets in shared memory)
 
 void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches);
-void launch_tone(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
-                 double* metrics, int tone_ctas, int wl, cudaStream_t st, long long* launches);
+void launch_tone_collect(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
+                         cudaStream_t st, long long* launches);
+void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items, int item_capacity, double* metrics,
+                       int tone_ctas, int wl, cudaStream_t st, long long* launches);
 void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches);
-void launch_chirp_fft(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* out, cudaStream_t st);
+void launch_tone_tables(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* chirp_fft,
+                        double2* pre, double2* post, cudaStream_t st);
 size_t tone_item_bytes();
 
 }  // namespace apd

@@ -75,7 +75,7 @@ k_verify_normal(VerifyArgs A)
         const int half = W / 2;                                            // apd.py:534-535
         if (pk + half > n + 5 || pk - half < -5) {                         // apd.py:541-546
             if (threadIdx.x == 0) {
-                init_record(*rec, A.chunk0 + unit.x, clip, pk, kind, q[pk]);
+                init_record(*rec, A.chunk0 + unit.x, clip, pk, kind, A.pk.peak_height[(long long)slot * A.pk.peak_stride + p]);
                 rec->flags |= APD_FLAG_SKIPPED;
             }
             continue;
@@ -165,7 +165,7 @@ k_verify_normal(VerifyArgs A)
             accept = r[center] >= kPearsonMin;                             // apd.py:897
         }
         if (threadIdx.x == 0) {
-            init_record(*rec, A.chunk0 + unit.x, clip, pk, kind, q[pk]);
+            init_record(*rec, A.chunk0 + unit.x, clip, pk, kind, A.pk.peak_height[(long long)slot * A.pk.peak_stride + p]);
             rec->similarity_whole = whole;
             rec->similarity_middle = middle;
             for (int w = 0; w < 3; ++w) rec->pearson[w] = r[w];
@@ -183,25 +183,54 @@ __device__ __forceinline__ double2 zmul(double2 a, double2 b)
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// In-place-semantics float64 FFT of length P (power of two) by one CTA, Stockham radix-2,
-// ping-ponging between x and y in global memory; returns the buffer holding the result.
-// tw[t] = e^{-2 pi i t / P}, t < P/2.  INV conjugates the twiddles (unnormalised inverse).
+// float64 FFT of length P (power of two) by one CTA: Stockham radix-4 passes (plus one radix-2 pass when
+// log2 P is odd), ping-ponging between x and y in global memory (L2 resident); returns the buffer
+// holding the result.  tw[t] = e^{-2 pi i t / P}, t < P/2.  INV conjugates the twiddles (unnormalised).
+__device__ __forceinline__ double2 tw_at(const double2* __restrict__ tw, int idx, int half, bool inv)
+{
+    double2 w = idx < half ? tw[idx] : tw[idx - half];
+    if (idx >= half) { w.x = -w.x; w.y = -w.y; }
+    if (inv) w.y = -w.y;
+    return w;
+}
+
 template <bool INV>
 __device__ double2* fft64(double2* x, double2* y, const double2* __restrict__ tw, int P)
 {
-    const int half = P >> 1;
-    int lg = 0;
-    for (int Ns = 1; Ns < P; Ns <<= 1, ++lg) {
-        const int tstep = half / Ns;
-        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const int half = P >> 1, quarter = P >> 2;
+    int Ns = 1;
+    while (Ns * 4 <= P) {
+        const int tstep = P / (4 * Ns);
+#pragma unroll 2
+        for (int j = threadIdx.x; j < quarter; j += blockDim.x) {
             const int k = j & (Ns - 1);
-            double2 w = tw[k * tstep];
-            if (INV) w.y = -w.y;
+            const double2 a0 = x[j];
+            double2 a1 = x[j + quarter], a2 = x[j + 2 * quarter], a3 = x[j + 3 * quarter];
+            if (Ns > 1) {
+                a1 = zmul(a1, tw_at(tw, k * tstep, half, INV));
+                a2 = zmul(a2, tw_at(tw, 2 * k * tstep, half, INV));
+                a3 = zmul(a3, tw_at(tw, 3 * k * tstep, half, INV));
+            }
+            const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
+            const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
+            // (+-i) * d13 : forward multiplies by -i, inverse by +i
+            const double2 r = INV ? make_double2(-d13.y, d13.x) : make_double2(d13.y, -d13.x);
+            const int o = (j / Ns) * 4 * Ns + k;
+            y[o] = make_double2(s02.x + s13.x, s02.y + s13.y);
+            y[o + Ns] = make_double2(d02.x + r.x, d02.y + r.y);
+            y[o + 2 * Ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
+            y[o + 3 * Ns] = make_double2(d02.x - r.x, d02.y - r.y);
+        }
+        __syncthreads();
+        double2* t = x; x = y; y = t;
+        Ns *= 4;
+    }
+    if (Ns < P) {                                   // one radix-2 pass left (Ns == P/2)
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
             const double2 a = x[j];
-            const double2 b = zmul(x[j + half], w);
-            const int o = ((j >> lg) << (lg + 1)) + k;
-            y[o] = make_double2(a.x + b.x, a.y + b.y);
-            y[o + Ns] = make_double2(a.x - b.x, a.y - b.y);
+            const double2 b = zmul(x[j + half], tw_at(tw, j, half, INV));     // k = j, tstep = 1
+            y[j] = make_double2(a.x + b.x, a.y + b.y);
+            y[j + Ns] = make_double2(a.x - b.x, a.y - b.y);
         }
         __syncthreads();
         double2* t = x; x = y; y = t;
@@ -217,9 +246,11 @@ __device__ __forceinline__ double2 chirp(long long n, int L, double sign)   // e
     return make_double2(c, s);
 }
 
-// Builds FFT_P of the wrapped chirp b[m] = e^{+i pi m^2 / L} (|m| < L) for one tone clip (init time).
+// Init-time tables of one tone clip: FFT_P of the wrapped chirp b[m] = e^{+i pi m^2 / L} (|m| < L),
+// pre[n] = hann_L[n] * e^{-i pi n^2 / L} and post[k] = e^{-i pi k^2 / L} (k <= L/2).
 __global__ void __launch_bounds__(1024)
-k_tone_chirp_fft(int L, int P, const double2* __restrict__ tw, double2* buf0, double2* buf1, double2* out)
+k_tone_tables(int L, int P, const double2* __restrict__ tw, double2* buf0, double2* buf1, double2* chirp_fft,
+              double2* pre, double2* post)
 {
     for (int m = threadIdx.x; m < P; m += blockDim.x) {
         double2 v = make_double2(0, 0);
@@ -227,29 +258,38 @@ k_tone_chirp_fft(int L, int P, const double2* __restrict__ tw, double2* buf0, do
         else if (P - m < L) v = chirp(P - m, L, +1.0);
         buf0[m] = v;
     }
+    for (int n = threadIdx.x; n < L; n += blockDim.x) {
+        const double h = L > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)n / (double)(L - 1)) : 1.0;    // np.hanning
+        const double2 c = chirp(n, L, -1.0);
+        pre[n] = make_double2(h * c.x, h * c.y);
+        if (n <= L / 2) post[n] = c;
+    }
     __syncthreads();
     const double2* r = fft64<false>(buf0, buf1, tw, P);
-    for (int m = threadIdx.x; m < P; m += blockDim.x) out[m] = r[m];
+    for (int m = threadIdx.x; m < P; m += blockDim.x) chirp_fft[m] = r[m];
 }
 
-struct ToneItem { int slot; int p; };
+struct ToneItem { int ci; int clip; int peak; float height; };
 
-__global__ void k_tone_worklist(VerifyArgs A, int nslots, ToneItem* items, int* n_items, int capacity)
+// Appends this round's tone-clip peaks to the batch-level work list (tone verification only needs
+// the raw audio + gain, so it is deferred to one launch per batch).
+__global__ void k_tone_collect(VerifyArgs A, int nslots, ToneItem* items, int* n_items, int capacity)
 {
-    // one thread: ordered list of (slot, peak) pairs of tone clips (few entries)
     if (blockIdx.x || threadIdx.x) return;
-    int cnt = 0;
+    int cnt = *n_items;
     for (int s = 0; s < nslots; ++s) {
         if (A.pk.slot0 + s >= *A.pk.sel_count) break;
-        const int clip = A.pk.sel[A.pk.slot0 + s].y;
-        if (!(A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0)) continue;
+        const int2 u = A.pk.sel[A.pk.slot0 + s];
+        if (!(A.cv.strategy[u.y] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[u.y] > 0.0)) continue;
         for (int p = 0; p < A.pk.n_peaks[s]; ++p) {
-            if (cnt < capacity) items[cnt] = ToneItem{s, p};
+            if (cnt < capacity)
+                items[cnt] = ToneItem{u.x, u.y, A.pk.peaks[(long long)s * A.pk.peak_stride + p],
+                                      A.pk.peak_height[(long long)s * A.pk.peak_stride + p]};
             ++cnt;
         }
     }
-    *n_items = cnt < capacity ? cnt : capacity;
-    if (cnt > capacity) atomicOr(A.pk.overflow, 2);
+    if (cnt > capacity) { atomicOr(A.pk.overflow, 2); cnt = capacity; }
+    *n_items = cnt;
 }
 
 // metrics[item][seg][5]
@@ -276,22 +316,22 @@ k_tone_metrics(VerifyArgs A, const ToneItem* __restrict__ items, const int* __re
     }
     __syncthreads();
     for (int it = blockIdx.y; it < *n_items; it += gridDim.y) {
-        const int slot = items[it].slot, p = items[it].p;
-        const int2 unit = A.pk.sel[A.pk.slot0 + slot];
-        const int clip = unit.y;
+        const ToneItem item = items[it];
+        const int clip = item.clip;
         const int g = A.pk.clip_group[clip];
         long long start;
         int nsec;
-        section_bounds(A.pk.geom[g], unit.x, start, nsec);
+        section_bounds(A.pk.geom[g], item.ci, start, nsec);
         const float* __restrict__ x = A.pk.geom[g].audio + (start - A.pk.geom[g].base);
-        const double gain = A.gains[(long long)unit.x * A.n_groups + g];
+        const double gain = A.gains[(long long)item.ci * A.n_groups + g];
         const int L = A.pk.clip_len[clip];
         const int P = A.cv.tone_P[clip];
         const double2* __restrict__ tw = A.cv.tone_tw[clip];
         const double2* __restrict__ cf = A.cv.tone_chirp_fft[clip];
+        const double2* __restrict__ pre = A.cv.tone_pre[clip];
+        const double2* __restrict__ post = A.cv.tone_post[clip];
         const double f0 = A.cv.tone_hz[clip];
-        const int pk = A.pk.peaks[(long long)slot * A.pk.peak_stride + p];
-        const int ms = pk - L + 1 + (seg == 1 ? -L : (seg == 2 ? L : 0));    // apd.py:650-653
+        const int ms = item.peak - L + 1 + (seg == 1 ? -L : (seg == 2 ? L : 0));    // apd.py:650-653
         double* out = metrics + ((long long)it * 3 + seg) * 5;
         const double band = fmax(40.0, f0 * 0.08), lock = fmax(20.0, f0 * 0.04);   // du.py:56-57
         const double d = __ddiv_rn(1.0, (double)sr);
@@ -304,9 +344,8 @@ k_tone_metrics(VerifyArgs A, const ToneItem* __restrict__ items, const int* __re
             if (n < L) {
                 const int k = ms + n;
                 const double xv = (k >= 0 && k < nsec) ? (double)normalize_sample(x[k], gain) : 0.0;
-                const double h = L > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)n / (double)(L - 1)) : 1.0;
-                const double2 c = chirp(n, L, -1.0);
-                v = make_double2(xv * h * c.x, xv * h * c.y);
+                const double2 c = pre[n];
+                v = make_double2(xv * c.x, xv * c.y);
             }
             buf0[n] = v;
         }
@@ -321,7 +360,7 @@ k_tone_metrics(VerifyArgs A, const ToneItem* __restrict__ items, const int* __re
         double tot = 0, bsum = 0, best = -1.0;
         int arg = 0x7fffffff;
         for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-            const double2 z = zmul(c[k], chirp(k, L, -1.0));
+            const double2 z = zmul(c[k], post[k]);
             const double re = z.x * invP, im = z.y * invP;
             const double m2 = re * re + im * im;
             tot += m2;
@@ -418,36 +457,46 @@ k_tone_metrics(VerifyArgs A, const ToneItem* __restrict__ items, const int* __re
     }
 }
 
+// Decision (apd.py:707-724) and record emission for the deferred tone candidates.
 __global__ void k_tone_decide(VerifyArgs A, const ToneItem* __restrict__ items, const int* __restrict__ n_items,
                               const double* __restrict__ metrics)
 {
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= *n_items) return;
-    const int slot = items[it].slot, p = items[it].p;
-    const int2 unit = A.pk.sel[A.pk.slot0 + slot];
-    const int clip = unit.y;
-    const int pk = A.pk.peaks[(long long)slot * A.pk.peak_stride + p];
+    const ToneItem item = items[it];
+    const int clip = item.clip;
     long long start;
     int nsec;
-    section_bounds(A.pk.geom[A.pk.clip_group[clip]], unit.x, start, nsec);
+    section_bounds(A.pk.geom[A.pk.clip_group[clip]], item.ci, start, nsec);
     const int L = A.pk.clip_len[clip];
     const int n = nsec + L - 1, half = (2 * L - 1) / 2;
-    apd_candidate* rec = A.slot_cands + (long long)slot * A.pk.peak_stride + p;
-    const float h = A.pk.corr[(long long)slot * A.pk.corr_stride + pk];
-    init_record(*rec, A.chunk0 + unit.x, clip, pk, 2, h);
-    if (pk + half > n + 5 || pk - half < -5) { rec->flags |= APD_FLAG_SKIPPED; return; }
-    const double* m = metrics + (long long)it * 15;
-    for (int s = 0; s < 3; ++s) for (int j = 0; j < 5; ++j) rec->tone[s][j] = m[s * 5 + j];
-    const double* th = A.cv.tone_thr + clip * 6;
-    const double f0 = A.cv.tone_hz[clip];
-    const double lo = fmin(m[5 + 1], m[10 + 1]), hi = fmax(m[5 + 1], m[10 + 1]);
-    bool ok = fabs(m[0] - f0) <= fmax(0.05 * fmax(fabs(m[0]), fabs(f0)), 0.0);   // apd.py:707
-    ok = ok && m[1] >= th[0] && m[2] >= th[1] && (long long)m[3] >= (long long)th[2] && m[4] >= th[3]
-            && lo <= th[4] && hi <= th[5];                                         // apd.py:717-724
-    if (ok) rec->flags |= APD_FLAG_ACCEPT;
+    apd_candidate rec;
+    init_record(rec, A.chunk0 + item.ci, clip, item.peak, 2, item.height);
+    if (item.peak + half > n + 5 || item.peak - half < -5) {
+        rec.flags |= APD_FLAG_SKIPPED;
+    } else {
+        const double* m = metrics + (long long)it * 15;
+        for (int s = 0; s < 3; ++s) for (int j = 0; j < 5; ++j) rec.tone[s][j] = m[s * 5 + j];
+        const double* th = A.cv.tone_thr + clip * 6;
+        const double f0 = A.cv.tone_hz[clip];
+        const double lo = fmin(m[5 + 1], m[10 + 1]), hi = fmax(m[5 + 1], m[10 + 1]);
+        bool ok = fabs(m[0] - f0) <= fmax(0.05 * fmax(fabs(m[0]), fabs(f0)), 0.0);   // apd.py:707
+        ok = ok && m[1] >= th[0] && m[2] >= th[1] && (long long)m[3] >= (long long)th[2] && m[4] >= th[3]
+                && lo <= th[4] && hi <= th[5];                                         // apd.py:717-724
+        if (ok) rec.flags |= APD_FLAG_ACCEPT;
+    }
+    const int o = atomicAdd(A.out_count, 1);
+    if (o < A.out_capacity) A.out[o] = rec;
+    else atomicOr(A.pk.overflow, 4);
 }
 
-// Ordered gather of the per-slot records into the output list.
+__device__ __forceinline__ bool is_tone_slot(const VerifyArgs& A, int s)
+{
+    const int clip = A.pk.sel[A.pk.slot0 + s].y;
+    return A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0;
+}
+
+// Ordered gather of the per-slot records (normal / short clips) into the output list.
 __global__ void __launch_bounds__(256)
 k_emit(VerifyArgs A, int nslots)
 {
@@ -456,13 +505,14 @@ k_emit(VerifyArgs A, int nslots)
         int off = *A.out_count;
         for (int s = 0; s < nslots; ++s) {
             s_off[s] = off;
-            if (A.pk.slot0 + s < *A.pk.sel_count) off += A.pk.n_peaks[s];
+            if (A.pk.slot0 + s < *A.pk.sel_count && !is_tone_slot(A, s)) off += A.pk.n_peaks[s];
         }
         s_off[nslots] = off;
     }
     __syncthreads();
     for (int s = 0; s < nslots; ++s) {
         if (A.pk.slot0 + s >= *A.pk.sel_count) break;
+        if (is_tone_slot(A, s)) continue;
         const int np = A.pk.n_peaks[s];
         for (int p = threadIdx.x; p < np; p += blockDim.x) {
             const int o = s_off[s] + p;
@@ -484,20 +534,27 @@ void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* 
     ++*launches;
 }
 
-void launch_tone(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
-                 double* metrics, int tone_ctas, int wl, cudaStream_t st, long long* launches)
+void launch_tone_collect(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
+                         cudaStream_t st, long long* launches)
 {
-    if (nslots <= 0 || tone_ctas <= 0) return;
+    if (nslots <= 0) return;
+    k_tone_collect<<<1, 32, 0, st>>>(A, nslots, (ToneItem*)items, n_items, item_capacity);
+    ++*launches;
+}
+
+void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items, int item_capacity, double* metrics,
+                       int tone_ctas, int wl, cudaStream_t st, long long* launches)
+{
+    if (tone_ctas <= 0) return;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_tone_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr = true;
     }
-    k_tone_worklist<<<1, 32, 0, st>>>(A, nslots, (ToneItem*)items, n_items, item_capacity);
     dim3 g(3, tone_ctas);
     k_tone_metrics<<<g, 1024, (size_t)2 * wl * sizeof(double2), st>>>(A, (const ToneItem*)items, n_items, metrics);
     k_tone_decide<<<(item_capacity + 127) / 128, 128, 0, st>>>(A, (const ToneItem*)items, n_items, metrics);
-    *launches += 3;
+    *launches += 2;
 }
 
 void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
@@ -509,9 +566,10 @@ void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* la
 
 size_t tone_item_bytes() { return sizeof(ToneItem); }
 
-void launch_chirp_fft(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* out, cudaStream_t st)
+void launch_tone_tables(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* chirp_fft,
+                        double2* pre, double2* post, cudaStream_t st)
 {
-    k_tone_chirp_fft<<<1, 1024, 0, st>>>(L, P, tw, buf0, buf1, out);
+    k_tone_tables<<<1, 1024, 0, st>>>(L, P, tw, buf0, buf1, chirp_fft, pre, post);
 }
 
 }  // namespace apd

@@ -105,3 +105,63 @@ def describe(patterns: list[dict[str, Any]], sr: int) -> dict[str, Any]:
     ls = [p["audio"].size for p in patterns]
     return {"n_patterns": len(patterns), "min_len": min(ls), "max_len": max(ls),
             "sliding_windows": sorted({math.ceil(l / sr) for l in ls})}
+
+
+def make_stream_device(seconds: float, patterns: list[dict[str, Any]], sr: int = 8000, seed: int = 0,
+                       plants_per_pattern: int = 24, chunk_seconds: int = 60, bed_sigma: float = 0.1,
+                       gains: tuple[float, ...] = (1.0, 0.5), device: str = "cuda"):
+    """Same recipe as :func:`make_stream` but generated on the GPU (config 3-5 scale: 24 h = 691 M samples).
+
+    Returns (float32 CUDA tensor, plants).  The noise bed comes from torch's device generator, so it
+    is reproducible per seed on a given torch build; plant offsets come from numpy RandomState."""
+    import torch
+    n = int(round(seconds * sr))
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    audio = torch.empty(n, dtype=torch.float32, device=device)
+    block = 1 << 26
+    taps = torch.tensor([0.5 ** (k + 1) for k in range(32)], dtype=torch.float32, device=device).flip(0).view(1, 1, -1)
+    prev = torch.zeros(31, dtype=torch.float32, device=device)
+    for a in range(0, n, block):
+        b = min(n, a + block)
+        w = torch.randn(b - a, generator=gen, dtype=torch.float32, device=device) * bed_sigma
+        x = torch.cat([prev, w])
+        audio[a:b] = torch.nn.functional.conv1d(x.view(1, 1, -1), taps).view(-1)   # one-pole low-pass, a = 0.5
+        prev = x[-31:].clone()
+    rs = np.random.RandomState(seed + 1000003)
+    C = int(chunk_seconds * sr)
+    plants: list[tuple[str, int, float]] = []
+    taken = np.zeros((n + C - 1) // C + 1, dtype=np.int32)   # coarse occupancy: at most a few plants per chunk
+    spans: list[tuple[int, int]] = []
+    for pi, p in enumerate(patterns):
+        L = p["audio"].size
+        if L + 2 >= n:
+            continue
+        pt = torch.from_numpy(p["audio"]).to(device)
+        for k in range(plants_per_pattern):
+            for _attempt in range(50):
+                if k % 6 == 0 and n > C + L:
+                    b0 = int(rs.randint(1, max(2, n // C))) * C
+                    start = b0 - int(rs.randint(1, L))
+                else:
+                    start = int(rs.randint(0, n - L - 1))
+                if start < 0 or start + L >= n:
+                    continue
+                pad = L if p.get("strategy") == "marker_tone" else 0
+                a0, a1 = max(0, start - pad), min(n, start + L + pad)
+                c0, c1 = a0 // C, a1 // C
+                if taken[c0:c1 + 1].max() >= 2:
+                    continue
+                if any(a0 < e and s < a1 for s, e in spans[-4096:] if abs(s - a0) < 4 * C):
+                    continue
+                break
+            else:
+                continue
+            taken[c0:c1 + 1] += 1
+            spans.append((a0, a1))
+            g = float(gains[(pi + k) % len(gains)])
+            duck = 0.02 if p.get("strategy") == "marker_tone" else 0.1
+            audio[a0:a1] *= duck
+            audio[start:start + L] += g * pt
+            plants.append((p["name"], start, g))
+    return audio, plants

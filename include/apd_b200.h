@@ -137,6 +137,12 @@ APD_API int apd_stage_peaks_verify(apd_ctx* ctx, void* cuda_stream);
 APD_API int apd_stage_unit_correlation(apd_ctx* ctx, int32_t chunk, int32_t clip, float* out_host, int32_t capacity,
                                int32_t* n_out, void* cuda_stream);
 
+/* Stage timing: when enabled, apd_scan brackets its four stages with CUDA events on the caller's
+ * stream and accumulates their device times (ms): [0] loudness, [1] forward FFT,
+ * [2] fused multiply + inverse FFT + |.| + max, [3] peaks + verification. */
+APD_API int apd_profile(apd_ctx* ctx, int enable);
+APD_API int apd_profile_read(apd_ctx* ctx, double* ms4, int reset);
+
 /* Introspection for the bench: algorithmic byte counts and kernel launch counter. */
 APD_API int64_t apd_launch_count(apd_ctx* ctx);
 APD_API int apd_unit_n_out(apd_ctx* ctx, int32_t chunk, int32_t clip, int64_t total_samples, int32_t* n_out);
