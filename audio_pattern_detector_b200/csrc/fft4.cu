@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdio>
 
+#include "fft_fast.cuh"
 #include "internal.h"
 
 namespace apd {
@@ -186,6 +187,208 @@ k_inv_cols(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, I
     }
 }
 
+// ------------------------------------------------------------------ fast kernels (hot shapes)
+// Row kernels handle N2 = 512 = 8*8*8 with 64 threads per row (one radix-8 butterfly per thread per
+// pass); column kernels handle N1 in {512 = 8*8*8, 640 = 8*8*10} with one thread per butterfly and
+// TB adjacent columns on the lanes.  See fft_fast.cuh.
+constexpr int kRowN = 512;
+constexpr int kRowPitch = kRowN + kRowN / 8;
+__device__ __forceinline__ int rpad(int e) { return e + (e >> 3); }
+
+template <int TR>
+__global__ void __launch_bounds__(TR * 64)
+k_inv_rows_fast(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U,
+                const float2* const* __restrict__ clip_spec, float2* __restrict__ W)
+{
+    __shared__ float2 tws[kRowN];
+    __shared__ float2 buf[TR * kRowPitch];
+    fill_twiddles(tws, kRowN);
+    const int u = blockIdx.y;
+    const int2 unit = get_unit(U, u);
+    const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
+    const int c = blockIdx.x * TR + q;
+    const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + (long long)c * kRowN;
+    const float2* __restrict__ hs = clip_spec[unit.y] + (long long)c * kRowN;
+    float2* b = buf + q * kRowPitch;
+    float2 v[8];
+    bfly_load<8, +1, kRowN, 1>(j, tws, [&](int e) { return cmul(xs[e], __ldg(&hs[e])); }, v);
+    bfly_store<8, 1>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
+    __syncthreads();
+    bfly_load<8, +1, kRowN, 8>(j, tws, [&](int e) { return b[rpad(e)]; }, v);
+    __syncthreads();
+    bfly_store<8, 8>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
+    __syncthreads();
+    bfly_load<8, +1, kRowN, 64>(j, tws, [&](int e) { return b[rpad(e)]; }, v);
+    // outputs b_idx = j + 64 r ; four-step twiddle w_M^{+b c} = base * step^r
+    const float invM = 1.0f / (float)P.M;
+    float2 pw[8];
+    unit_powers<8>(twiddle_frac(64 * c, invM, +1.0f), pw);
+    const float2 base = twiddle_frac(j * c, invM, +1.0f);
+    float2* __restrict__ out = W + (long long)u * P.M + (long long)c * kRowN;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) out[j + 64 * r] = cmul(v[r], cmul(base, pw[r]));
+}
+
+template <int TR>
+__global__ void __launch_bounds__(TR * 64)
+k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ spec, long long spec_stride)
+{
+    __shared__ float2 tws[kRowN];
+    __shared__ float2 buf[TR * kRowPitch];
+    fill_twiddles(tws, kRowN);
+    const int sec = blockIdx.y;
+    const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
+    const int c = blockIdx.x * TR + q;
+    const float2* __restrict__ in = T + (long long)sec * P.M + (long long)c * kRowN;
+    float2* b = buf + q * kRowPitch;
+    float2 v[8];
+    bfly_load<8, -1, kRowN, 1>(j, tws, [&](int e) { return in[e]; }, v);
+    bfly_store<8, 1>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
+    __syncthreads();
+    bfly_load<8, -1, kRowN, 8>(j, tws, [&](int e) { return b[rpad(e)]; }, v);
+    __syncthreads();
+    bfly_store<8, 8>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
+    __syncthreads();
+    bfly_load<8, -1, kRowN, 64>(j, tws, [&](int e) { return b[rpad(e)]; }, v);
+    float2* __restrict__ out = spec + (long long)sec * spec_stride + (long long)c * kRowN;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) out[j + 64 * r] = v[r];
+}
+
+// Column kernels: S::N = N1, TB adjacent columns, threads = TB * (N1 / 8).
+template <class S, int TB>
+__global__ void __launch_bounds__(TB * (S::N / 8))
+k_fwd_cols_fast(Fft4Plan P, SectionGeom G, const double* __restrict__ gains, int gain_stride, float2* __restrict__ T)
+{
+    constexpr int N1 = S::N;
+    __shared__ float2 tws[N1];
+    __shared__ float2 buf[N1 * TB];
+    fill_twiddles(tws, N1);
+    const int sec = blockIdx.y;
+    const int q = threadIdx.x % TB, j = threadIdx.x / TB;
+    const int bcol = blockIdx.x * TB + q;
+    long long start;
+    int n;
+    section_bounds(G, sec, start, n);
+    const float* __restrict__ x = G.audio + (start - G.base);
+    const double gain = gains ? gains[(long long)sec * gain_stride] : 1.0;
+    const int M = P.M, N2 = P.N2;
+    const float invN = 1.0f / (2.0f * (float)M);
+    float2 v[10];
+    {
+        // pre-twiddle e^{-i pi m / N}, m = (j + r T) N2 + b  = base * (e^{-i pi / (2 R0)})^r
+        constexpr int T0 = N1 / S::R0;
+        float2 pw[S::R0];
+        unit_powers<S::R0>(cispif(-0.5f / (float)S::R0), pw);
+        const float2 base = cispif(-(float)(j * N2 + bcol) * invN);
+        bfly_load<S::R0, -1, N1, 1>(j, tws, [&](int e) {
+            const int m = e * N2 + bcol;
+            const float x0 = m < n ? normalize_sample(x[m], gain) : 0.0f;
+            const float x1 = m + M < n ? normalize_sample(x[m + M], gain) : 0.0f;
+            return cmul(make_float2(x0, -x1), cmul(base, pw[(e - j) / T0]));
+        }, v);
+    }
+    bfly_store<S::R0, 1>(j, [&](int e, float2 y) { buf[e * TB + q] = y; }, v);
+    __syncthreads();
+    bfly_load<S::R1, -1, N1, S::R0>(j, tws, [&](int e) { return buf[e * TB + q]; }, v);
+    __syncthreads();
+    bfly_store<S::R1, S::R0>(j, [&](int e, float2 y) { buf[e * TB + q] = y; }, v);
+    __syncthreads();
+    if (j < N1 / S::R2) {
+        bfly_load<S::R2, -1, N1, S::R0 * S::R1>(j, tws, [&](int e) { return buf[e * TB + q]; }, v);
+        // outputs c = j + r * (N1/R2); twiddle w_M^{-b c} = base * step^r
+        const float invM = 1.0f / (float)M;
+        float2 pw[S::R2];
+        unit_powers<S::R2>(twiddle_frac(bcol * (N1 / S::R2), invM, -1.0f), pw);
+        const float2 base = twiddle_frac(bcol * j, invM, -1.0f);
+        float2* __restrict__ out = T + (long long)sec * M;
+#pragma unroll
+        for (int r = 0; r < S::R2; ++r)
+            out[(long long)(j + r * (N1 / S::R2)) * N2 + bcol] = cmul(v[r], cmul(base, pw[r]));
+    }
+}
+
+template <class S, int TB, bool WRITE>
+__global__ void __launch_bounds__(TB * (S::N / 8))
+k_inv_cols_fast(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, InvOut O)
+{
+    constexpr int N1 = S::N;
+    __shared__ float2 tws[N1];
+    __shared__ float2 buf[N1 * TB];
+    __shared__ float red[32];
+    fill_twiddles(tws, N1);
+    const int u = blockIdx.y;
+    const int2 unit = get_unit(U, u);
+    const int q = threadIdx.x % TB, j = threadIdx.x / TB;
+    const int bcol = blockIdx.x * TB + q;
+    const int M = P.M, N2 = P.N2;
+    const float2* __restrict__ in = W + (long long)u * M;
+    float2 v[10];
+    bfly_load<S::R0, +1, N1, 1>(j, tws, [&](int e) { return in[(long long)e * N2 + bcol]; }, v);
+    bfly_store<S::R0, 1>(j, [&](int e, float2 y) { buf[e * TB + q] = y; }, v);
+    __syncthreads();
+    bfly_load<S::R1, +1, N1, S::R0>(j, tws, [&](int e) { return buf[e * TB + q]; }, v);
+    __syncthreads();
+    bfly_store<S::R1, S::R0>(j, [&](int e, float2 y) { buf[e * TB + q] = y; }, v);
+    __syncthreads();
+    float best = 0.0f;
+    if (j < N1 / S::R2) {
+        bfly_load<S::R2, +1, N1, S::R0 * S::R1>(j, tws, [&](int e) { return buf[e * TB + q]; }, v);
+        long long start;
+        int n;
+        section_bounds(G, unit.x, start, n);
+        const int n_out = n > 0 ? n + O.clip_len[unit.y] - 1 : 0;
+        const float invN = 1.0f / (2.0f * (float)M);
+        const float invM = 1.0f / (float)M;
+        // post-twiddle e^{+i pi m / N}, m = (j + r N1/R2) N2 + b = base * (e^{i pi / (2 R2)})^r
+        float2 pw[S::R2];
+        unit_powers<S::R2>(cispif(0.5f / (float)S::R2), pw);
+        const float2 base = cispif((float)(j * N2 + bcol) * invN);
+        float mc = 1.0f;
+        float* __restrict__ corr = nullptr;
+        if (WRITE) {
+            const float um = __uint_as_float(O.unit_max_bits[(long long)unit.x * O.n_clips + unit.y]);
+            mc = fmaxf(O.self_max[unit.y], um);                       // apd.py:493
+            corr = O.corr + (long long)u * O.corr_stride;
+        }
+#pragma unroll
+        for (int r = 0; r < S::R2; ++r) {
+            const int m = (j + r * (N1 / S::R2)) * N2 + bcol;
+            const float2 z = cmul(v[r], cmul(base, pw[r]));
+            const float y0 = fabsf(z.x * invM), y1 = fabsf(z.y * invM);
+            if (WRITE) {
+                if (m < n_out) corr[m] = y0 / mc;                      // apd.py:494 (float32 divide)
+                if (m + M < n_out) corr[m + M] = y1 / mc;
+            } else {
+                if (m < n_out) best = fmaxf(best, y0);
+                if (m + M < n_out) best = fmaxf(best, y1);
+            }
+        }
+    }
+    if (!WRITE) {
+        best = warp_max(best);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0)
+                atomicMax(&O.unit_max_bits[(long long)unit.x * O.n_clips + unit.y], __float_as_uint(t));
+        }
+    }
+}
+
+constexpr int kFastTR = 4;     // rows per CTA  (256 threads)
+constexpr int kFastTB = 8;     // columns per CTA (512 / 640 threads)
+
+static int fast_shape(const Fft4Plan& P)
+{
+    if (P.N2 != kRowN) return 0;
+    if (P.N1 == 512) return 512;
+    if (P.N1 == 640) return 640;
+    return 0;
+}
+
 // ------------------------------------------------------------------ plans
 static bool factor(int n, SubPlan* sp)
 {
@@ -242,7 +445,8 @@ bool build_plan(int M_min, Fft4Plan* plan, std::string* err)
             const long long M = (long long)n1 * n2;
             if (M < M_min) continue;
             const double skew = std::fabs(std::log2((double)n1 / (double)n2));
-            const double cost = (double)M * (1.0 + 0.03 * skew);
+            double cost = (double)M * (1.0 + 0.03 * skew);
+            if (n2 == kRowN && (n1 == 512 || n1 == 640)) cost *= 0.6;      // register-resident fast kernels exist
             if (cost < best_cost) { best_cost = cost; bN1 = n1; bN2 = n2; }
         }
     if (!bN1) {
@@ -299,6 +503,16 @@ void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains
 {
     if (nsec <= 0) return;
     ensure_attrs();
+    const int fs = fast_shape(P);
+    if (fs) {
+        dim3 gc(P.N2 / kFastTB, nsec), gr(P.N1 / kFastTR, nsec);
+        if (fs == 512)
+            k_fwd_cols_fast<Shape512, kFastTB><<<gc, kFastTB * 64, 0, st>>>(P, G, gains, gain_stride, scratch);
+        else
+            k_fwd_cols_fast<Shape640, kFastTB><<<gc, kFastTB * 80, 0, st>>>(P, G, gains, gain_stride, scratch);
+        k_fwd_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, scratch, spec, spec_stride);
+        return;
+    }
     dim3 gc(P.N2 >> P.tb_log2, nsec), gr(P.N1 >> P.tr_log2, nsec);
     k_fwd_cols<<<gc, P.threads, P.smem_col, st>>>(P, G, gains, gain_stride, scratch);
     k_fwd_rows<<<gr, P.threads, P.smem_row, st>>>(P, scratch, spec, spec_stride);
@@ -310,6 +524,16 @@ void launch_inverse_max(const Fft4Plan& P, const SectionGeom& G, const float2* s
 {
     if (nunits <= 0) return;
     ensure_attrs();
+    const int fs = fast_shape(P);
+    if (fs) {
+        dim3 gr(P.N1 / kFastTR, nunits), gc(P.N2 / kFastTB, nunits);
+        k_inv_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
+        if (fs == 512)
+            k_inv_cols_fast<Shape512, kFastTB, false><<<gc, kFastTB * 64, 0, st>>>(P, G, U, scratch, out);
+        else
+            k_inv_cols_fast<Shape640, kFastTB, false><<<gc, kFastTB * 80, 0, st>>>(P, G, U, scratch, out);
+        return;
+    }
     dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);
     k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
     k_inv_cols<false><<<gc, P.threads, P.smem_col, st>>>(P, G, U, scratch, out);
@@ -321,6 +545,16 @@ void launch_inverse_write(const Fft4Plan& P, const SectionGeom& G, const float2*
 {
     if (nunits <= 0) return;
     ensure_attrs();
+    const int fs = fast_shape(P);
+    if (fs) {
+        dim3 gr(P.N1 / kFastTR, nunits), gc(P.N2 / kFastTB, nunits);
+        k_inv_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
+        if (fs == 512)
+            k_inv_cols_fast<Shape512, kFastTB, true><<<gc, kFastTB * 64, 0, st>>>(P, G, U, scratch, out);
+        else
+            k_inv_cols_fast<Shape640, kFastTB, true><<<gc, kFastTB * 80, 0, st>>>(P, G, U, scratch, out);
+        return;
+    }
     dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);
     k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
     k_inv_cols<true><<<gc, P.threads, P.smem_col, st>>>(P, G, U, scratch, out);

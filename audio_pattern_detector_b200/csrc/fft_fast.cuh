@@ -1,0 +1,99 @@
+// Register-resident three-pass sub-FFTs for the hot four-step shapes.
+//
+// Each pass is a Stockham radix-R step in which a thread owns one whole butterfly in
+// registers.  The FIRST pass reads its R inputs straight from global memory and the LAST
+// pass hands its R outputs straight to the epilogue (global store / reduction), so shared
+// memory is touched only by the two inter-pass exchanges.  The thread -> (transform q,
+// butterfly j) mapping is chosen per kernel so that those direct global accesses are
+// contiguous: row kernels put j on the lanes (a warp covers 256 contiguous bytes of a row),
+// column kernels put q on the lanes (a warp covers 32..64-byte row segments of adjacent
+// columns).
+//
+// Exchange buffer layouts:
+//   column kernels : buf[e * TB + q]                      (q on lanes: conflict free)
+//   row kernels    : buf[q * PITCH + e + (e >> 3)]        (1 pad per 8 elements: the 8- and
+//                                                          64-element strides of radix-8 passes
+//                                                          fall on distinct banks)
+#pragma once
+#include "fft_sub.cuh"
+
+namespace apd {
+
+template <int SIGN> struct Dft<10, SIGN> {
+    static __device__ __forceinline__ void run(float2* v)
+    {
+        float2 e[5] = {v[0], v[2], v[4], v[6], v[8]};
+        float2 o[5] = {v[1], v[3], v[5], v[7], v[9]};
+        Dft<5, SIGN>::run(e);
+        Dft<5, SIGN>::run(o);
+        // w10^k = cos(pi k/5) + SIGN i sin(pi k/5)
+        const float c1 = 0.80901699437494742410f, s1 = 0.58778525229247312917f;
+        const float c2 = 0.30901699437494742410f, s2 = 0.95105651629515357212f;
+        const float2 w1 = make_float2(c1, SIGN * s1), w2 = make_float2(c2, SIGN * s2);
+        const float2 w3 = make_float2(-c2, SIGN * s2), w4 = make_float2(-c1, SIGN * s1);
+        const float2 t0 = o[0], t1 = cmul(o[1], w1), t2 = cmul(o[2], w2), t3 = cmul(o[3], w3), t4 = cmul(o[4], w4);
+        v[0] = cadd(e[0], t0); v[5] = csub(e[0], t0);
+        v[1] = cadd(e[1], t1); v[6] = csub(e[1], t1);
+        v[2] = cadd(e[2], t2); v[7] = csub(e[2], t2);
+        v[3] = cadd(e[3], t3); v[8] = csub(e[3], t3);
+        v[4] = cadd(e[4], t4); v[9] = csub(e[4], t4);
+    }
+};
+
+template <int N_, int R0_, int R1_, int R2_> struct Shape3 {
+    static constexpr int N = N_, R0 = R0_, R1 = R1_, R2 = R2_;
+    static_assert(R0_ * R1_ * R2_ == N_, "radices must multiply to N");
+    static constexpr int MAXB = (N_ / R0_ > N_ / R2_ ? (N_ / R0_ > N_ / R1_ ? N_ / R0_ : N_ / R1_)
+                                                       : (N_ / R2_ > N_ / R1_ ? N_ / R2_ : N_ / R1_));
+};
+using Shape512 = Shape3<512, 8, 8, 8>;
+using Shape640 = Shape3<640, 8, 8, 10>;
+
+// powers w^0..w^(R-1) of a unit complex number (tree: depth log2 R)
+template <int R>
+__device__ __forceinline__ void unit_powers(float2 w, float2* p)
+{
+    p[0] = make_float2(1.0f, 0.0f);
+    if (R > 1) p[1] = w;
+#pragma unroll
+    for (int r = 2; r < R; ++r) p[r] = cmul(p[r >> 1], p[r - (r >> 1)]);
+}
+
+// One radix-R Stockham pass for butterfly j of a transform, split in two halves so a single
+// exchange buffer can be used (all loads of a pass complete before any store of that pass):
+//   bfly_load : v[r] = LD(j + r*T), inter-pass twiddle, R-point DFT   (results stay in registers)
+//   bfly_store: ST(j0 + r*NS, v[r])
+template <int R, int SIGN, int N, int NS, class LD>
+__device__ __forceinline__ void bfly_load(int j, const float2* __restrict__ tws, LD ld, float2* v)
+{
+    constexpr int T = N / R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ld(j + r * T);
+    if (NS > 1) {
+        const int k = j % NS;
+        constexpr int tstep = N / (NS * R);
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            float2 w = tws[k * r * tstep];
+            if (SIGN > 0) w.y = -w.y;
+            v[r] = cmul(v[r], w);
+        }
+    }
+    Dft<R, SIGN>::run(v);
+}
+
+template <int R, int NS, class ST>
+__device__ __forceinline__ void bfly_store(int j, ST st, const float2* v)
+{
+    const int j0 = (j / NS) * NS * R + (j % NS);
+#pragma unroll
+    for (int r = 0; r < R; ++r) st(j0 + r * NS, v[r]);
+}
+
+__device__ __forceinline__ void fill_twiddles(float2* tws, int n)
+{
+    const float inv = 1.0f / (float)n;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) tws[t] = cispif(-2.0f * (float)t * inv);
+}
+
+}  // namespace apd
