@@ -52,11 +52,16 @@ struct ClipHost {
 struct Group {
     int sw = 0, halo = 0;
     std::vector<int> clips;
-    Fft4Plan plan;
+    int shape = 0;                  // index into apd_ctx::shapes
     long long spec_off = 0;
-    int* d_clips = nullptr;
-    int2* d_sel = nullptr;
     int max_L = 0;
+};
+
+// Clips whose groups share one four-step FFT shape are correlated by the same launches.
+struct ShapeClass {
+    Fft4Plan plan;
+    std::vector<int> clips;
+    int* d_clips = nullptr;
 };
 
 template <typename T>
@@ -105,23 +110,27 @@ __global__ void k_window_max(const float* __restrict__ cc, int lo, int hi, int d
     }
 }
 
-__global__ void k_select_group(const unsigned int* __restrict__ unit_max_bits, const float* __restrict__ self_max,
-                               const int* __restrict__ group_clips, int ng, int n_clips, int n_chunks, float height,
-                               int2* __restrict__ sel, int* __restrict__ sel_count)
+// Ordered compaction (one CTA) of the units of one shape class whose normalised maximum reaches the
+// height threshold: only those can have a peak (every other sample of the unit is smaller).
+// Appends to sel[] starting at *begin (end of the previous shape's units) and writes the new end.
+__global__ void __launch_bounds__(1024)
+k_select_shape(const unsigned int* __restrict__ unit_max_bits, const float* __restrict__ self_max,
+               const int* __restrict__ shape_clips, int ns, int n_clips, int n_chunks, float height,
+               int2* __restrict__ sel, const int* __restrict__ begin, int* __restrict__ end, int capacity,
+               int* __restrict__ overflow)
 {
-    // ordered compaction by one CTA over the dense (ci, clip-in-group) units of one group
     __shared__ int warp_tot[32];
     __shared__ int base;
-    if (threadIdx.x == 0) base = 0;
+    if (threadIdx.x == 0) base = *begin;
     __syncthreads();
-    const int n_units = n_chunks * ng;
+    const int n_units = n_chunks * ns;
     for (int u0 = 0; u0 < n_units; u0 += blockDim.x) {
         const int u = u0 + threadIdx.x;
         bool pass = false;
         int ci = 0, clip = 0;
         if (u < n_units) {
-            ci = u / ng;
-            clip = group_clips[u % ng];
+            ci = u / ns;
+            clip = shape_clips[u % ns];
             const float am = __uint_as_float(unit_max_bits[(long long)ci * n_clips + clip]);
             const float mc = fmaxf(self_max[clip], am);
             pass = mc > 0.0f && (am / mc) >= height;
@@ -132,7 +141,10 @@ __global__ void k_select_group(const unsigned int* __restrict__ unit_max_bits, c
         __syncthreads();
         int off = base;
         for (int i = 0; i < w; ++i) off += warp_tot[i];
-        if (pass) sel[off + __popc(bal & ((1u << lane) - 1))] = make_int2(ci, clip);
+        if (pass) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1));
+            if (pos < capacity) sel[pos] = make_int2(ci, clip);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
@@ -141,7 +153,10 @@ __global__ void k_select_group(const unsigned int* __restrict__ unit_max_bits, c
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *sel_count = base;
+    if (threadIdx.x == 0) {
+        if (base > capacity) { atomicOr(overflow, 8); base = capacity; }
+        *end = base;
+    }
 }
 
 __global__ void k_record_npeaks(const int2* __restrict__ sel, const int* __restrict__ sel_count, int slot0, int nslots,
@@ -161,6 +176,8 @@ struct apd_ctx {
     float height = kDefaultHeight;
     std::vector<ClipHost> clips;
     std::vector<Group> groups;
+    std::vector<ShapeClass> shapes;
+    int max_halo = 0;
     KwConfig kw{};
     std::map<int, Fft4Plan> self_plans;
     long long launches = 0;
@@ -177,12 +194,16 @@ struct apd_ctx {
     const double2** d_tone_tw_ptrs = nullptr;
     const double2** d_tone_pre_ptrs = nullptr;
     const double2** d_tone_post_ptrs = nullptr;
+    long long* d_clip_spec_off = nullptr;
+    int2* d_sel = nullptr;                // selected (ci, clip) units of the batch, shape-class major
+    int sel_capacity = 0;
     SectionGeom* d_geoms = nullptr;
     SectionGeom* h_geoms = nullptr;       // pinned
 
     // workspace
     int cells_stride = 0;
-    double *d_kw_state = nullptr, *d_kw_energy = nullptr, *d_kw_em1 = nullptr, *d_lufs = nullptr, *d_gain = nullptr;
+    double *d_kw_state = nullptr, *d_kw_energy = nullptr, *d_kw_em1 = nullptr, *d_kw_patch = nullptr;
+    double *d_lufs = nullptr, *d_gain = nullptr;
     long long spec_slab = 0;              // complex elements per chunk (sum of group M)
     float2* d_spec = nullptr;
     long long scratch_elems = 0;
@@ -190,7 +211,9 @@ struct apd_ctx {
     int inv_units = 0;                    // units per inverse launch
     unsigned int* d_unit_max = nullptr;
     int* d_unit_npeaks = nullptr;
-    int* d_counts = nullptr;              // [G] selected counts, [G] = out_count, [G+1] = overflow, [G+2] tone items
+    // device counters: [0..S] begin of each shape class in d_sel ([S] = total selected),
+    //                  [S+1] candidates emitted, [S+2] overflow flags, [S+3] tone work items
+    int* d_counts = nullptr;
     int* h_counts = nullptr;              // pinned mirror
     int n_slots = 0;
     long long corr_stride = 0, cand_stride = 0;
@@ -238,10 +261,31 @@ static void fill_geoms(apd_ctx* c)
     }
 }
 
+static SectionGeom union_geom(const apd_ctx* c)
+{
+    SectionGeom G = c->h_geoms[0];
+    G.halo = c->max_halo;
+    return G;
+}
+
+static UnitCtx unit_ctx(const apd_ctx* c)
+{
+    return UnitCtx{c->d_geoms, c->d_clip_group, c->d_clip_len, c->d_clip_spec_off, c->d_clip_spec_ptrs};
+}
+
 extern "C" const char* apd_last_error(void) { return g_err.c_str(); }
 
-static int self_correlation(apd_ctx* c, ClipHost& cl, unsigned int* d_tmp_max, int* d_tmp_int, float* d_zero_f,
-                            const float2** d_tmp_ptr)
+// |corr(clip, clip)| / max through the same kernels as the sections (reference apd.py:373-383).
+struct InitTmp {
+    unsigned int* max_bits = nullptr;     // [1]
+    int* ints = nullptr;                  // [0] = 0 (clip index / group), [1] = clip length
+    float* zero_f = nullptr;              // [1] = 0
+    const float2** spec_ptr = nullptr;    // [1]
+    long long* zero_ll = nullptr;         // [1] = 0
+    SectionGeom* geom = nullptr;          // [1]
+};
+
+static int self_correlation(apd_ctx* c, ClipHost& cl, InitTmp& t)
 {
     const int L = cl.L;
     const int M_min = L < 16 ? 16 : L;                       // real length 2M >= 2L-1
@@ -260,18 +304,19 @@ static int self_correlation(apd_ctx* c, ClipHost& cl, unsigned int* d_tmp_max, i
     SectionGeom Ga{cl.d_norm, 0, L, L, 0, 0}, Gb{cl.d_rev, 0, L, L, 0, 0};
     launch_forward(P, Ga, nullptr, 0, 1, scr, sa, P.M, 0);
     launch_forward(P, Gb, nullptr, 0, 1, scr, sb, P.M, 0);
-    CK(cudaMemset(d_tmp_max, 0, sizeof(unsigned int)));
-    const int Lh = L;
-    CK(cudaMemcpy(d_tmp_int + 1, &Lh, sizeof(int), cudaMemcpyHostToDevice));   // [0] = clip index 0, [1] = length
+    CK(cudaMemset(t.max_bits, 0, sizeof(unsigned int)));
+    CK(cudaMemcpy(t.ints + 1, &L, sizeof(int), cudaMemcpyHostToDevice));
     const float2* hp = sb;
-    CK(cudaMemcpy(d_tmp_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice));
-    UnitSrc U{nullptr, d_tmp_int, 1, 0};
-    InvOut O{d_tmp_max, 1, cl.d_self_corr, (long long)(2 * L - 1), d_zero_f, d_tmp_int + 1};
-    launch_inverse_max(P, Ga, sa, P.M, U, 1, d_tmp_ptr, scr, O, 0);
-    launch_inverse_write(P, Ga, sa, P.M, U, 1, d_tmp_ptr, scr, O, 0);
+    CK(cudaMemcpy(t.spec_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.geom, &Ga, sizeof(Ga), cudaMemcpyHostToDevice));
+    UnitSrc U{nullptr, nullptr, t.ints, 1, 0};                // dense: unit 0 = (section 0, clip 0)
+    UnitCtx X{t.geom, t.ints, t.ints + 1, t.zero_ll, t.spec_ptr};
+    InvOut O{t.max_bits, 1, cl.d_self_corr, (long long)(2 * L - 1), t.zero_f};
+    launch_inverse(P, X, sa, P.M, U, 1, scr, O, false, 0);
+    launch_inverse(P, X, sa, P.M, U, 1, scr, O, true, 0);
     CK(cudaDeviceSynchronize());
     unsigned int bits = 0;
-    CK(cudaMemcpy(&bits, d_tmp_max, sizeof(bits), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&bits, t.max_bits, sizeof(bits), cudaMemcpyDeviceToHost));
     memcpy(&cl.self_max, &bits, sizeof(float));
     c->launches += 8;
     cudaFree(sa);
@@ -330,31 +375,50 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     for (auto& g : c->groups) {
         const long long n_out = c->C + g.halo + g.max_L - 1;
         max_nout = std::max(max_nout, n_out);
-        if (plan_min_M_for(n_out) > (1LL << 21) || !build_plan((int)plan_min_M_for(n_out), &g.plan, &err)) {
+        c->max_halo = std::max(c->max_halo, g.halo);
+        Fft4Plan plan;
+        if (plan_min_M_for(n_out) > (1LL << 21) || !build_plan((int)plan_min_M_for(n_out), &plan, &err)) {
             delete c;
             return fail(APD_ERR_UNSUPPORTED, err.empty() ? "chunk too long for the FFT plan" : err);
         }
+        int shape = -1;
+        for (size_t k = 0; k < c->shapes.size(); ++k)
+            if (c->shapes[k].plan.N1 == plan.N1 && c->shapes[k].plan.N2 == plan.N2) shape = (int)k;
+        if (shape < 0) {
+            ShapeClass sc;
+            sc.plan = plan;
+            c->shapes.push_back(sc);
+            shape = (int)c->shapes.size() - 1;
+        } else {
+            free_plan(&plan);
+        }
+        g.shape = shape;
+        for (int p : g.clips) c->shapes[shape].clips.push_back(p);
         g.spec_off = c->spec_slab;
-        c->spec_slab += g.plan.M;
-        max_M = std::max<long long>(max_M, g.plan.M);
-        CK(upload(&g.d_clips, g.clips));
-        CK(dalloc(&g.d_sel, (size_t)c->maxB * g.clips.size()));
+        c->spec_slab += c->shapes[shape].plan.M;
+        max_M = std::max<long long>(max_M, c->shapes[shape].plan.M);
     }
+    for (auto& sc : c->shapes) {
+        std::sort(sc.clips.begin(), sc.clips.end());
+        CK(upload(&sc.d_clips, sc.clips));
+    }
+    const int S = (int)c->shapes.size();
 
     // ---- pattern-side precompute on the device
-    unsigned int* d_tmp_max = nullptr;
-    int* d_tmp_int = nullptr;
-    float* d_zero_f = nullptr;
-    const float2** d_tmp_ptr = nullptr;
-    double *d_tl = nullptr, *d_tg = nullptr, *d_tstate = nullptr, *d_ten = nullptr, *d_tem1 = nullptr;
-    CK(dalloc(&d_tmp_max, 1));
-    CK(dalloc(&d_tmp_int, 2));
-    CK(cudaMemset(d_tmp_int, 0, 2 * sizeof(int)));
-    CK(dalloc(&d_zero_f, 1));
-    CK(cudaMemset(d_zero_f, 0, sizeof(float)));
-    CK(dalloc(&d_tmp_ptr, 1));
+    InitTmp tmp;
+    double *d_tl = nullptr, *d_tg = nullptr, *d_tstate = nullptr, *d_ten = nullptr, *d_tem1 = nullptr, *d_tpatch = nullptr;
+    CK(dalloc(&tmp.max_bits, 1));
+    CK(dalloc(&tmp.ints, 2));
+    CK(cudaMemset(tmp.ints, 0, 2 * sizeof(int)));
+    CK(dalloc(&tmp.zero_f, 1));
+    CK(cudaMemset(tmp.zero_f, 0, sizeof(float)));
+    CK(dalloc(&tmp.spec_ptr, 1));
+    CK(dalloc(&tmp.zero_ll, 1));
+    CK(cudaMemset(tmp.zero_ll, 0, sizeof(long long)));
+    CK(dalloc(&tmp.geom, 1));
     CK(dalloc(&d_tl, 1));
     CK(dalloc(&d_tg, 1));
+    CK(dalloc(&d_tpatch, (size_t)c->kw.patch_cells));
     int max_L = 0;
     for (auto& cl : c->clips) max_L = std::max(max_L, cl.L);
     const int clip_cells = (max_L + c->kw.cell - 1) / c->kw.cell + 1;
@@ -371,23 +435,24 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         CK(cudaMemcpy(cl.d_raw, descs[p].samples, sizeof(float) * L, cudaMemcpyHostToDevice));
         // loudness with block = clip_seconds if < 0.5 else 0.4 (apd.py:169-171): same rule as a section
         SectionGeom Gc{cl.d_raw, 0, L, L, 0, 0};
-        launch_loudness(c->kw, Gc, 1, 0, clip_cells, d_tstate, d_ten, d_tem1, d_tl, d_tg, 1, 0);
+        CK(cudaMemcpy(tmp.geom, &Gc, sizeof(Gc), cudaMemcpyHostToDevice));
+        launch_loudness(c->kw, Gc, &Gc, tmp.geom, 1, 1, clip_cells, d_tstate, d_ten, d_tem1, d_tpatch, d_tl, d_tg, 0);
         k_prepare_clip<<<std::min(256, (L + 255) / 256), 256>>>(cl.d_raw, L, d_tg, cl.d_norm, cl.d_rev);
         CK(cudaMemcpy(&cl.lufs, d_tl, sizeof(double), cudaMemcpyDeviceToHost));
         c->launches += 5;
         // spectrum of the reversed clip at the group's FFT size
-        Group& g = c->groups[cl.group];
-        CK(dalloc(&cl.d_spec, (size_t)g.plan.M));
+        const Fft4Plan& gplan = c->shapes[c->groups[cl.group].shape].plan;
+        CK(dalloc(&cl.d_spec, (size_t)gplan.M));
         {
             float2* scr = nullptr;
-            CK(dalloc(&scr, (size_t)g.plan.M));
+            CK(dalloc(&scr, (size_t)gplan.M));
             SectionGeom Gr{cl.d_rev, 0, L, L, 0, 0};
-            launch_forward(g.plan, Gr, nullptr, 0, 1, scr, cl.d_spec, g.plan.M, 0);
+            launch_forward(gplan, Gr, nullptr, 0, 1, scr, cl.d_spec, gplan.M, 0);
             CK(cudaDeviceSynchronize());
             cudaFree(scr);
             c->launches += 2;
         }
-        int rc = self_correlation(c, cl, d_tmp_max, d_tmp_int, d_zero_f, d_tmp_ptr);
+        int rc = self_correlation(c, cl, tmp);
         if (rc != APD_OK) return rc;
     }
 
@@ -482,8 +547,14 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(upload(&c->d_tone_tw_ptrs, h_tw));
     CK(upload(&c->d_tone_pre_ptrs, h_pre));
     CK(upload(&c->d_tone_post_ptrs, h_post));
-    cudaFree(d_tmp_max); cudaFree(d_tmp_int); cudaFree(d_zero_f); cudaFree((void*)d_tmp_ptr);
-    cudaFree(d_tl); cudaFree(d_tg); cudaFree(d_tstate); cudaFree(d_ten); cudaFree(d_tem1);
+    cudaFree(tmp.max_bits); cudaFree(tmp.ints); cudaFree(tmp.zero_f); cudaFree((void*)tmp.spec_ptr);
+    cudaFree(tmp.zero_ll); cudaFree(tmp.geom);
+    cudaFree(d_tl); cudaFree(d_tg); cudaFree(d_tstate); cudaFree(d_ten); cudaFree(d_tem1); cudaFree(d_tpatch);
+    {
+        std::vector<long long> h_off(n_clips);
+        for (int p = 0; p < n_clips; ++p) h_off[p] = c->groups[c->clips[p].group].spec_off;
+        CK(upload(&c->d_clip_spec_off, h_off));
+    }
 
     // ---- workspace
     const int B = c->maxB;
@@ -492,20 +563,24 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     long long max_sec = c->C;
     for (auto& g : c->groups) max_sec = std::max(max_sec, c->C + g.halo);
     c->cells_stride = (int)((max_sec + c->kw.cell - 1) / c->kw.cell + 1);
-    CK(dalloc(&c->d_kw_state, (size_t)B * G * c->cells_stride * 4));
-    CK(dalloc(&c->d_kw_energy, (size_t)B * G * c->cells_stride));
-    CK(dalloc(&c->d_kw_em1, (size_t)B * G));
+    CK(dalloc(&c->d_kw_state, (size_t)B * c->cells_stride * 4));
+    CK(dalloc(&c->d_kw_energy, (size_t)B * c->cells_stride));
+    CK(dalloc(&c->d_kw_em1, (size_t)B));
+    CK(dalloc(&c->d_kw_patch, (size_t)B * G * c->kw.patch_cells));
     CK(dalloc(&c->d_lufs, (size_t)B * G));
     CK(dalloc(&c->d_gain, (size_t)B * G));
     CK(dalloc(&c->d_spec, (size_t)B * c->spec_slab));
+    c->n_slots = 256;
     c->inv_units = 512;
-    c->scratch_elems = std::max<long long>((long long)B, c->inv_units) * max_M;
+    if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
+    c->scratch_elems = std::max<long long>(std::max<long long>(B, c->inv_units), c->n_slots) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
     CK(dalloc(&c->d_unit_max, (size_t)B * n_clips));
     CK(dalloc(&c->d_unit_npeaks, (size_t)B * n_clips));
-    CK(dalloc(&c->d_counts, (size_t)G + 4));
-    CK(cudaMallocHost((void**)&c->h_counts, sizeof(int) * (G + 4)));
-    c->n_slots = 256;
+    CK(dalloc(&c->d_counts, (size_t)S + 4));
+    CK(cudaMallocHost((void**)&c->h_counts, sizeof(int) * (S + 4)));
+    c->sel_capacity = B * n_clips;
+    CK(dalloc(&c->d_sel, (size_t)c->sel_capacity));
     c->corr_stride = (max_nout + 31) / 32 * 32;
     c->cand_stride = max_nout / 2 + 2;
     c->peak_stride = (int)std::min<long long>(max_nout / std::max(min_L, 1) + 2, 8192);
@@ -546,13 +621,14 @@ extern "C" int apd_destroy(apd_ctx* c)
         cudaFree(cl.d_self_corr); cudaFree(cl.d_win_cache); cudaFree(cl.d_tone_chirp); cudaFree(cl.d_tone_tw);
         cudaFree(cl.d_tone_pre); cudaFree(cl.d_tone_post);
     }
-    for (auto& g : c->groups) { free_plan(&g.plan); cudaFree(g.d_clips); cudaFree(g.d_sel); }
+    for (auto& sc : c->shapes) { free_plan(&sc.plan); cudaFree(sc.d_clips); }
     for (auto& kv : c->self_plans) free_plan(&kv.second);
     kw_config_destroy(&c->kw);
     void* ptrs[] = {c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
                     c->d_win_ds, c->d_tone_P, c->d_self_max, (void*)c->d_self_corr_ptrs, (void*)c->d_win_cache_ptrs,
                     (void*)c->d_clip_spec_ptrs, c->d_tone_hz, c->d_tone_thr, (void*)c->d_tone_chirp_ptrs,
                     (void*)c->d_tone_tw_ptrs, (void*)c->d_tone_pre_ptrs, (void*)c->d_tone_post_ptrs, c->d_peak_height,
+                    c->d_clip_spec_off, c->d_sel, c->d_kw_patch,
                     c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
                     c->d_gain, c->d_spec, c->d_scratch, c->d_unit_max, c->d_unit_npeaks, c->d_counts, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
@@ -573,7 +649,7 @@ extern "C" int apd_clip_info(apd_ctx* c, int clip, int32_t* sw, double* lufs, fl
     if (sw) *sw = cl.sw;
     if (lufs) *lufs = cl.lufs;
     if (self_max) *self_max = cl.self_max;
-    if (fft_points) *fft_points = 2 * c->groups[cl.group].plan.M;
+    if (fft_points) *fft_points = 2 * c->shapes[c->groups[cl.group].shape].plan.M;
     return APD_OK;
 }
 
@@ -601,9 +677,7 @@ static int stage_begin(apd_ctx* c, const float* audio, int64_t base, int64_t n, 
 {
     if (!c || !audio || n <= 0 || ce <= cb || cb < 0) return fail(APD_ERR_INVALID, "scan: bad arguments");
     if (ce - cb > c->maxB) return fail(APD_ERR_INVALID, "scan: more chunks than max_batch_chunks");
-    int max_halo = 0;
-    for (auto& g : c->groups) max_halo = std::max(max_halo, g.halo);
-    if (cb > 0 && (long long)cb * c->C - max_halo < base)
+    if (cb > 0 && (long long)cb * c->C - c->max_halo < base)
         return fail(APD_ERR_INVALID, "scan: audio region does not contain the look-back halo of chunk_begin");
     if (cb == 0 && base != 0) return fail(APD_ERR_INVALID, "scan: chunk 0 requires base_sample == 0");
     if ((long long)(ce - 1) * c->C >= base + n) return fail(APD_ERR_INVALID, "scan: chunk_end beyond the audio region");
@@ -614,7 +688,7 @@ static int stage_begin(apd_ctx* c, const float* audio, int64_t base, int64_t n, 
     const int B = ce - cb;
     CK(cudaMemsetAsync(c->d_unit_max, 0, sizeof(unsigned int) * (size_t)B * c->n_clips, st));
     CK(cudaMemsetAsync(c->d_unit_npeaks, 0xff, sizeof(int) * (size_t)B * c->n_clips, st));
-    CK(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * (c->groups.size() + 4), st));
+    CK(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * (c->shapes.size() + 4), st));
     c->staged = true;
     return APD_OK;
 }
@@ -622,11 +696,9 @@ static int stage_begin(apd_ctx* c, const float* audio, int64_t base, int64_t n, 
 static int stage_loudness(apd_ctx* c, cudaStream_t st)
 {
     const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
-    for (int g = 0; g < G; ++g) {
-        launch_loudness(c->kw, c->h_geoms[g], B, g * B, c->cells_stride, c->d_kw_state, c->d_kw_energy,
-                        c->d_kw_em1, c->d_lufs + g, c->d_gain + g, G, st);
-        c->launches += 4;
-    }
+    launch_loudness(c->kw, union_geom(c), c->h_geoms, c->d_geoms, G, B, c->cells_stride, c->d_kw_state,
+                    c->d_kw_energy, c->d_kw_em1, c->d_kw_patch, c->d_lufs, c->d_gain, st);
+    c->launches += 5;
     CK(cudaGetLastError());
     return APD_OK;
 }
@@ -636,8 +708,8 @@ static int stage_forward(apd_ctx* c, cudaStream_t st)
     const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
     for (int g = 0; g < G; ++g) {
         Group& gr = c->groups[g];
-        launch_forward(gr.plan, c->h_geoms[g], c->d_gain + g, G, B, c->d_scratch, c->d_spec + gr.spec_off,
-                       c->spec_slab, st);
+        launch_forward(c->shapes[gr.shape].plan, c->h_geoms[g], c->d_gain + g, G, B, c->d_scratch,
+                       c->d_spec + gr.spec_off, c->spec_slab, st);
         c->launches += 2;
     }
     CK(cudaGetLastError());
@@ -646,16 +718,16 @@ static int stage_forward(apd_ctx* c, cudaStream_t st)
 
 static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
 {
-    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
-    InvOut O{c->d_unit_max, c->n_clips, nullptr, 0, c->d_self_max, c->d_clip_len};
-    for (int g = 0; g < G; ++g) {
-        Group& gr = c->groups[g];
-        const int ng = (int)gr.clips.size();
-        const int nunits = B * ng;
+    const int B = c->chunk_end - c->chunk_begin;
+    InvOut O{c->d_unit_max, c->n_clips, nullptr, 0, c->d_self_max};
+    const UnitCtx X = unit_ctx(c);
+    for (auto& sc : c->shapes) {
+        const int ns = (int)sc.clips.size();
+        const int nunits = B * ns;
         for (int u0 = 0; u0 < nunits; u0 += c->inv_units) {
-            UnitSrc U{nullptr, gr.d_clips, ng, u0};
-            launch_inverse_max(gr.plan, c->h_geoms[g], c->d_spec + gr.spec_off, c->spec_slab, U,
-                               std::min(c->inv_units, nunits - u0), c->d_clip_spec_ptrs, c->d_scratch, O, st);
+            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, u0};
+            launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, std::min(c->inv_units, nunits - u0),
+                           c->d_scratch, O, false, st);
             c->launches += 2;
         }
     }
@@ -663,59 +735,67 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
     return APD_OK;
 }
 
+// One phase-2 round: slots [slot0, slot0 + n_slots) of the selected list.
+static void phase2_round(apd_ctx* c, int slot0, cudaStream_t st)
+{
+    const int S = (int)c->shapes.size(), G = (int)c->groups.size();
+    const int ns = c->n_slots;
+    const UnitCtx X = unit_ctx(c);
+    InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
+    for (int s = 0; s < S; ++s) {
+        UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0};
+        launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch, O, true, st);
+        c->launches += 2;
+    }
+    PeakArgs PA{c->d_sel, c->d_counts + S, slot0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
+                c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
+                c->d_peaks, c->d_peak_height, c->peak_stride, c->d_n_peaks, c->d_n_cands, c->d_counts + S + 2};
+    launch_find_peaks(PA, ns, st);
+    ++c->launches;
+    ClipVerify CV{c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_self_corr_ptrs, c->d_win_lo,
+                  c->d_win_hi, c->d_win_ds, c->d_win_cache_ptrs, c->d_is_short, c->d_tone_hz, c->d_tone_thr,
+                  c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs, c->d_tone_pre_ptrs, c->d_tone_post_ptrs};
+    VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + S + 1, c->out_capacity,
+                  c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
+    launch_verify(VA, ns, st, &c->launches);
+    if (c->tone_ctas > 0)
+        launch_tone_collect(VA, ns, c->d_tone_items, c->d_counts + S + 3, c->tone_item_cap, st, &c->launches);
+    launch_emit(VA, ns, st, &c->launches);
+    k_record_npeaks<<<(ns + 127) / 128, 128, 0, st>>>(c->d_sel, c->d_counts + S, slot0, ns, c->d_n_peaks,
+                                                     c->n_clips, c->d_unit_npeaks);
+    ++c->launches;
+}
+
+static void phase2_tone(apd_ctx* c, cudaStream_t st)
+{
+    if (c->tone_ctas <= 0) return;
+    const int S = (int)c->shapes.size(), G = (int)c->groups.size();
+    PeakArgs PA{c->d_sel, c->d_counts + S, 0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
+                c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
+                c->d_peaks, c->d_peak_height, c->peak_stride, c->d_n_peaks, c->d_n_cands, c->d_counts + S + 2};
+    ClipVerify CV{c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_self_corr_ptrs, c->d_win_lo,
+                  c->d_win_hi, c->d_win_ds, c->d_win_cache_ptrs, c->d_is_short, c->d_tone_hz, c->d_tone_thr,
+                  c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs, c->d_tone_pre_ptrs, c->d_tone_post_ptrs};
+    VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + S + 1, c->out_capacity,
+                  c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
+    launch_tone_batch(VA, c->d_tone_items, c->d_counts + S + 3, c->tone_item_cap, c->d_tone_metrics,
+                      c->tone_ctas, c->tone_wl, st, &c->launches);
+}
+
+// Select the units that can have peaks, then run the first phase-2 round without waiting for the
+// count (CTAs beyond it exit at once); collect() runs further rounds in the rare case that more than
+// n_slots units of a batch were selected.
 static int stage_peaks_verify(apd_ctx* c, cudaStream_t st)
 {
-    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
-    for (int g = 0; g < G; ++g) {
-        Group& gr = c->groups[g];
-        k_select_group<<<1, 1024, 0, st>>>(c->d_unit_max, c->d_self_max, gr.d_clips, (int)gr.clips.size(),
-                                           c->n_clips, B, c->height, gr.d_sel, c->d_counts + g);
+    const int B = c->chunk_end - c->chunk_begin, S = (int)c->shapes.size();
+    for (int s = 0; s < S; ++s) {
+        ShapeClass& sc = c->shapes[s];
+        k_select_shape<<<1, 1024, 0, st>>>(c->d_unit_max, c->d_self_max, sc.d_clips, (int)sc.clips.size(),
+                                           c->n_clips, B, c->height, c->d_sel, c->d_counts + s, c->d_counts + s + 1,
+                                           c->sel_capacity, c->d_counts + S + 2);
         ++c->launches;
     }
-    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    bool any_tone = false;
-    VerifyArgs last_va{};
-    for (int g = 0; g < G; ++g) {
-        Group& gr = c->groups[g];
-        const int cnt = c->h_counts[g];
-        for (int u0 = 0; u0 < cnt; u0 += c->n_slots) {
-            const int ns = std::min(c->n_slots, cnt - u0);
-            UnitSrc U{gr.d_sel, nullptr, 0, u0};
-            InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max, c->d_clip_len};
-            launch_inverse_write(gr.plan, c->h_geoms[g], c->d_spec + gr.spec_off, c->spec_slab, U, ns,
-                                 c->d_clip_spec_ptrs, c->d_scratch, O, st);
-            c->launches += 2;
-            PeakArgs PA{gr.d_sel, c->d_counts + g, u0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
-                        c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
-                        c->d_peaks, c->d_peak_height, c->peak_stride, c->d_n_peaks, c->d_n_cands,
-                        c->d_counts + G + 1};
-            launch_find_peaks(PA, ns, st);
-            ++c->launches;
-            ClipVerify CV{c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_self_corr_ptrs, c->d_win_lo,
-                          c->d_win_hi, c->d_win_ds, c->d_win_cache_ptrs, c->d_is_short, c->d_tone_hz, c->d_tone_thr,
-                          c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs, c->d_tone_pre_ptrs,
-                          c->d_tone_post_ptrs};
-            VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + G, c->out_capacity,
-                          c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
-            launch_verify(VA, ns, st, &c->launches);
-            bool group_has_tone = false;
-            for (int p : gr.clips)
-                group_has_tone |= c->clips[p].strategy == APD_STRATEGY_MARKER_TONE && c->clips[p].tone_hz > 0.0;
-            if (group_has_tone) {
-                launch_tone_collect(VA, ns, c->d_tone_items, c->d_counts + G + 2, c->tone_item_cap, st, &c->launches);
-                any_tone = true;
-            }
-            last_va = VA;
-            launch_emit(VA, ns, st, &c->launches);
-            k_record_npeaks<<<(ns + 127) / 128, 128, 0, st>>>(gr.d_sel, c->d_counts + g, u0, ns, c->d_n_peaks,
-                                                             c->n_clips, c->d_unit_npeaks);
-            ++c->launches;
-        }
-    }
-    if (any_tone)     // all tone candidates of the batch in one launch (they only read raw audio + gains)
-        launch_tone_batch(last_va, c->d_tone_items, c->d_counts + G + 2, c->tone_item_cap, c->d_tone_metrics,
-                          c->tone_ctas, c->tone_wl, st, &c->launches);
+    phase2_round(c, 0, st);
     CK(cudaGetLastError());
     return APD_OK;
 }
@@ -753,12 +833,16 @@ static bool cand_less(const apd_candidate& a, const apd_candidate& b)
 static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
                    double* lufs_host, cudaStream_t st)
 {
-    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
-    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (G + 4), cudaMemcpyDeviceToHost, st));
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size(), S = (int)c->shapes.size();
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const int n = c->h_counts[G];
-    if (c->h_counts[G + 1]) return fail(APD_ERR_OVERFLOW, "candidate workspace overflow (flags " +
-                                        std::to_string(c->h_counts[G + 1]) + ")");
+    for (int slot0 = c->n_slots; slot0 < c->h_counts[S]; slot0 += c->n_slots) phase2_round(c, slot0, st);
+    phase2_tone(c, st);
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int n = c->h_counts[S + 1];
+    if (c->h_counts[S + 2]) return fail(APD_ERR_OVERFLOW, "candidate workspace overflow (flags " +
+                                        std::to_string(c->h_counts[S + 2]) + ")");
     if (n > cap) return fail(APD_ERR_OVERFLOW, "candidate buffer too small");
     if (n > 0) {
         CK(cudaMemcpyAsync(cand_host, c->d_out, sizeof(apd_candidate) * n, cudaMemcpyDeviceToHost, st));
@@ -836,7 +920,7 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
     if (!c || !c->staged || clip < 0 || clip >= c->n_clips || chunk < c->chunk_begin || chunk >= c->chunk_end)
         return fail(APD_ERR_INVALID, "unit_correlation: bad unit");
     const ClipHost& cl = c->clips[clip];
-    Group& gr = c->groups[cl.group];
+    const Fft4Plan& plan = c->shapes[c->groups[cl.group].shape].plan;
     long long s;
     int ns;
     section_bounds(c->h_geoms[cl.group], chunk - c->chunk_begin, s, ns);
@@ -844,16 +928,20 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
     if (no > capacity) return fail(APD_ERR_INVALID, "unit_correlation: buffer too small");
     int2 u = make_int2(chunk - c->chunk_begin, clip);
     int2* d_u = nullptr;
+    int* d_rng = nullptr;
+    const int rng[2] = {0, 1};
     CK(dalloc(&d_u, 1));
+    CK(dalloc(&d_rng, 2));
     CK(cudaMemcpyAsync(d_u, &u, sizeof(u), cudaMemcpyHostToDevice, st));
-    UnitSrc U{d_u, nullptr, 0, 0};
-    InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max, c->d_clip_len};
-    launch_inverse_write(gr.plan, c->h_geoms[cl.group], c->d_spec + gr.spec_off, c->spec_slab, U, 1,
-                         c->d_clip_spec_ptrs, c->d_scratch, O, st);
+    CK(cudaMemcpyAsync(d_rng, rng, sizeof(rng), cudaMemcpyHostToDevice, st));
+    UnitSrc U{d_u, d_rng, nullptr, 0, 0};
+    InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
+    launch_inverse(plan, unit_ctx(c), c->d_spec, c->spec_slab, U, 1, c->d_scratch, O, true, st);
     c->launches += 2;
     CK(cudaMemcpyAsync(out_host, c->d_corr, sizeof(float) * no, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_u);
+    cudaFree(d_rng);
     *n_out = no;
     return APD_OK;
 }

@@ -93,8 +93,8 @@ k_fwd_rows(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ spec, 
 }
 
 __global__ void __launch_bounds__(512)
-k_inv_rows(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U,
-           const float2* const* __restrict__ clip_spec, float2* __restrict__ W)
+k_inv_rows(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U, UnitCtx C,
+           float2* __restrict__ W)
 {
     extern __shared__ float2 smem[];
     const int TR = 1 << P.tr_log2;
@@ -102,10 +102,12 @@ k_inv_rows(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, U
     float2* A = smem;
     float2* B = smem + P.N2 * LD;
     const int u = blockIdx.y;
-    const int2 unit = get_unit(U, u);
+    int2 unit;
+    if (!get_unit(U, u, &unit)) return;
     const int c0 = blockIdx.x * TR;
-    const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + (long long)c0 * P.N2;
-    const float2* __restrict__ hs = clip_spec[unit.y] + (long long)c0 * P.N2;
+    const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + C.clip_spec_off[unit.y] +
+                                    (long long)c0 * P.N2;
+    const float2* __restrict__ hs = C.clip_spec[unit.y] + (long long)c0 * P.N2;
     const int total = P.N2 << P.tr_log2;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int e = idx & (P.N2 - 1);
@@ -125,7 +127,7 @@ k_inv_rows(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, U
 
 template <bool WRITE>
 __global__ void __launch_bounds__(512)
-k_inv_cols(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, InvOut O)
+k_inv_cols(Fft4Plan P, UnitCtx C, UnitSrc U, const float2* __restrict__ W, InvOut O)
 {
     extern __shared__ float2 smem[];
     __shared__ float red[16];
@@ -133,7 +135,8 @@ k_inv_cols(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, I
     float2* A = smem;
     float2* B = smem + P.N1 * TB;
     const int u = blockIdx.y;
-    const int2 unit = get_unit(U, u);
+    int2 unit;
+    if (!get_unit(U, u, &unit)) return;
     const int b0 = blockIdx.x * TB;
     const int M = P.M;
     const float2* __restrict__ in = W + (long long)u * M;
@@ -148,8 +151,8 @@ k_inv_cols(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, I
 
     long long start;
     int n;
-    section_bounds(G, unit.x, start, n);
-    const int n_out = n > 0 ? n + O.clip_len[unit.y] - 1 : 0;
+    section_bounds(C.geoms[C.clip_group[unit.y]], unit.x, start, n);
+    const int n_out = n > 0 ? n + C.clip_len[unit.y] - 1 : 0;
     const float invN = 1.0f / (2.0f * (float)M);
     const float invM = 1.0f / (float)M;
     float mc = 1.0f;
@@ -197,18 +200,20 @@ __device__ __forceinline__ int rpad(int e) { return e + (e >> 3); }
 
 template <int TR>
 __global__ void __launch_bounds__(TR * 64)
-k_inv_rows_fast(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U,
-                const float2* const* __restrict__ clip_spec, float2* __restrict__ W)
+k_inv_rows_fast(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U, UnitCtx C,
+                float2* __restrict__ W)
 {
     __shared__ float2 tws[kRowN];
     __shared__ float2 buf[TR * kRowPitch];
-    fill_twiddles(tws, kRowN);
     const int u = blockIdx.y;
-    const int2 unit = get_unit(U, u);
+    int2 unit;
+    if (!get_unit(U, u, &unit)) return;
+    fill_twiddles(tws, kRowN);
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
     const int c = blockIdx.x * TR + q;
-    const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + (long long)c * kRowN;
-    const float2* __restrict__ hs = clip_spec[unit.y] + (long long)c * kRowN;
+    const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + C.clip_spec_off[unit.y] +
+                                    (long long)c * kRowN;
+    const float2* __restrict__ hs = C.clip_spec[unit.y] + (long long)c * kRowN;
     float2* b = buf + q * kRowPitch;
     float2 v[8];
     bfly_load<8, +1, kRowN, 1>(j, tws, [&](int e) { return cmul(xs[e], __ldg(&hs[e])); }, v);
@@ -310,15 +315,16 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, const double* __restrict__ gains, int
 
 template <class S, int TB, bool WRITE>
 __global__ void __launch_bounds__(TB * (S::N / 8))
-k_inv_cols_fast(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__ W, InvOut O)
+k_inv_cols_fast(Fft4Plan P, UnitCtx C, UnitSrc U, const float2* __restrict__ W, InvOut O)
 {
     constexpr int N1 = S::N;
     __shared__ float2 tws[N1];
     __shared__ float2 buf[N1 * TB];
     __shared__ float red[32];
-    fill_twiddles(tws, N1);
     const int u = blockIdx.y;
-    const int2 unit = get_unit(U, u);
+    int2 unit;
+    if (!get_unit(U, u, &unit)) return;
+    fill_twiddles(tws, N1);
     const int q = threadIdx.x % TB, j = threadIdx.x / TB;
     const int bcol = blockIdx.x * TB + q;
     const int M = P.M, N2 = P.N2;
@@ -336,8 +342,8 @@ k_inv_cols_fast(Fft4Plan P, SectionGeom G, UnitSrc U, const float2* __restrict__
         bfly_load<S::R2, +1, N1, S::R0 * S::R1>(j, tws, [&](int e) { return buf[e * TB + q]; }, v);
         long long start;
         int n;
-        section_bounds(G, unit.x, start, n);
-        const int n_out = n > 0 ? n + O.clip_len[unit.y] - 1 : 0;
+        section_bounds(C.geoms[C.clip_group[unit.y]], unit.x, start, n);
+        const int n_out = n > 0 ? n + C.clip_len[unit.y] - 1 : 0;
         const float invN = 1.0f / (2.0f * (float)M);
         const float invM = 1.0f / (float)M;
         // post-twiddle e^{+i pi m / N}, m = (j + r N1/R2) N2 + b = base * (e^{i pi / (2 R2)})^r
@@ -518,46 +524,28 @@ void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains
     k_fwd_rows<<<gr, P.threads, P.smem_row, st>>>(P, scratch, spec, spec_stride);
 }
 
-void launch_inverse_max(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
-                        const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch,
-                        const InvOut& out, cudaStream_t st)
+void launch_inverse(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab,
+                    const UnitSrc& U, int nunits, float2* scratch, const InvOut& out, bool write, cudaStream_t st)
 {
     if (nunits <= 0) return;
     ensure_attrs();
     const int fs = fast_shape(P);
     if (fs) {
         dim3 gr(P.N1 / kFastTR, nunits), gc(P.N2 / kFastTB, nunits);
-        k_inv_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
-        if (fs == 512)
-            k_inv_cols_fast<Shape512, kFastTB, false><<<gc, kFastTB * 64, 0, st>>>(P, G, U, scratch, out);
-        else
-            k_inv_cols_fast<Shape640, kFastTB, false><<<gc, kFastTB * 80, 0, st>>>(P, G, U, scratch, out);
+        k_inv_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, spec, spec_slab, U, C, scratch);
+        if (fs == 512) {
+            if (write) k_inv_cols_fast<Shape512, kFastTB, true><<<gc, kFastTB * 64, 0, st>>>(P, C, U, scratch, out);
+            else k_inv_cols_fast<Shape512, kFastTB, false><<<gc, kFastTB * 64, 0, st>>>(P, C, U, scratch, out);
+        } else {
+            if (write) k_inv_cols_fast<Shape640, kFastTB, true><<<gc, kFastTB * 80, 0, st>>>(P, C, U, scratch, out);
+            else k_inv_cols_fast<Shape640, kFastTB, false><<<gc, kFastTB * 80, 0, st>>>(P, C, U, scratch, out);
+        }
         return;
     }
     dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);
-    k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
-    k_inv_cols<false><<<gc, P.threads, P.smem_col, st>>>(P, G, U, scratch, out);
-}
-
-void launch_inverse_write(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
-                          const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch,
-                          const InvOut& out, cudaStream_t st)
-{
-    if (nunits <= 0) return;
-    ensure_attrs();
-    const int fs = fast_shape(P);
-    if (fs) {
-        dim3 gr(P.N1 / kFastTR, nunits), gc(P.N2 / kFastTB, nunits);
-        k_inv_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
-        if (fs == 512)
-            k_inv_cols_fast<Shape512, kFastTB, true><<<gc, kFastTB * 64, 0, st>>>(P, G, U, scratch, out);
-        else
-            k_inv_cols_fast<Shape640, kFastTB, true><<<gc, kFastTB * 80, 0, st>>>(P, G, U, scratch, out);
-        return;
-    }
-    dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);
-    k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_stride, U, clip_spec, scratch);
-    k_inv_cols<true><<<gc, P.threads, P.smem_col, st>>>(P, G, U, scratch, out);
+    k_inv_rows<<<gr, P.threads, P.smem_row, st>>>(P, spec, spec_slab, U, C, scratch);
+    if (write) k_inv_cols<true><<<gc, P.threads, P.smem_col, st>>>(P, C, U, scratch, out);
+    else k_inv_cols<false><<<gc, P.threads, P.smem_col, st>>>(P, C, U, scratch, out);
 }
 
 }  // namespace apd

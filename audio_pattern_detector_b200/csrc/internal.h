@@ -42,20 +42,37 @@ __host__ __device__ inline void section_bounds(const SectionGeom& g, int ci, lon
     n = end_abs > start_abs ? (int)(end_abs - start_abs) : 0;
 }
 
-// How the CTAs of an inverse launch find their (section, clip) unit.
+// How the CTAs of an inverse launch find their (section, clip) unit.  A launch serves every clip
+// whose sliding-window group uses the same FFT shape ("shape class").
 struct UnitSrc {
-    const int2* list;        // explicit (ci, clip) pairs, or nullptr for the dense layout below
-    const int* group_clips;  // dense: clip = group_clips[u % ng], ci = u / ng
-    int ng;
+    const int2* list;        // explicit (ci, clip) pairs (phase 2), or nullptr for the dense layout below
+    const int* list_begin;   // phase 2: this launch owns list positions [list_begin[0], list_begin[1])
+    const int* shape_clips;  // dense: clip = shape_clips[u % ns], ci = u / ns
+    int ns;
     int u0;                  // first unit of this launch (offset into list / dense numbering)
 };
 
-__device__ __forceinline__ int2 get_unit(const UnitSrc& s, int u)
+// Returns false if launch-local unit u is not this launch's to process.
+__device__ __forceinline__ bool get_unit(const UnitSrc& s, int u, int2* unit)
 {
     u += s.u0;
-    if (s.list) return s.list[u];
-    return make_int2(u / s.ng, s.group_clips[u % s.ng]);
+    if (s.list) {
+        if (u < s.list_begin[0] || u >= s.list_begin[1]) return false;
+        *unit = s.list[u];
+        return true;
+    }
+    *unit = make_int2(u / s.ns, s.shape_clips[u % s.ns]);
+    return true;
 }
+
+// Per-clip tables + per-group geometry needed to place a unit's data.
+struct UnitCtx {
+    const SectionGeom* geoms;        // [group] (device)
+    const int* clip_group;           // [clip]
+    const int* clip_len;             // [clip]
+    const long long* clip_spec_off;  // [clip] offset of the clip's group spectrum inside a chunk's slab
+    const float2* const* clip_spec;  // [clip] spectrum of the reversed, normalised clip
+};
 
 struct InvOut {
     // phase 1: per-unit maximum of |corr| (float bits, atomicMax), indexed ci * n_clips + clip
@@ -65,7 +82,6 @@ struct InvOut {
     float* corr;
     long long corr_stride;
     const float* self_max;   // per clip
-    const int* clip_len;     // per clip
 };
 
 bool build_plan(int M_min, Fft4Plan* plan, std::string* err);                 // picks N1, N2 >= M_min
@@ -74,11 +90,9 @@ long long plan_min_M_for(long long n_out);
 
 void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains, int gain_stride, int nsec,
                     float2* scratch /* nsec*M */, float2* spec, long long spec_stride, cudaStream_t st);
-void launch_inverse_max(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
-                        const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch /* nunits*M */,
-                        const InvOut& out, cudaStream_t st);
-void launch_inverse_write(const Fft4Plan& P, const SectionGeom& G, const float2* spec, long long spec_stride,
-                          const UnitSrc& U, int nunits, const float2* const* clip_spec, float2* scratch,
-                          const InvOut& out, cudaStream_t st);
+// Fused spectral multiply + inverse FFT + |.| ; write == false: per-unit max, write == true: normalised
+// correlation into O.corr.  scratch holds nunits * M complex (launch-local unit index).
+void launch_inverse(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab,
+                    const UnitSrc& U, int nunits, float2* scratch, const InvOut& out, bool write, cudaStream_t st);
 
 }  // namespace apd

@@ -14,6 +14,13 @@
 //           (-10 LU) gates, LUFS, gain = 10^((-16 - LUFS)/20)        (one warp per section)
 // which is the same linear recurrence re-associated, all in float64.
 //
+// Sharing across sliding-window groups: all groups of a chunk end at the same sample and differ only
+// in how far they look back, so passes A/scan/B run ONCE per chunk over the longest look-back
+// ("union" section).  A shorter group starts from zero state at a later sample t0; the K-weighting
+// filters forget their state within `patch_cells` cells (n r^n < 1e-20 for the slowest pole), so only
+// those first cells are re-filtered from zero state (k_kw_patch) and every later cell energy is, to
+// float64 rounding, the union's.
+//
 // Restriction: the gating hop 0.1*sr must be an integer number of samples
 // (sr % 10 == 0) so that block edges fall on cell edges; apd_create rejects other rates.
 #include <cmath>
@@ -40,7 +47,7 @@ __device__ __forceinline__ void kw_step(const double* cf, double x, double& s1, 
 //         (and energy_m1[sec] = energy of the last cell without its final sample).
 template <int PASS>
 __global__ void __launch_bounds__(128)
-k_kw_cells(KwConfig K, SectionGeom G, int sec0, int cells_stride, double* __restrict__ state,
+k_kw_cells(KwConfig K, SectionGeom G, int cells_stride, double* __restrict__ state,
            double* __restrict__ energy, double* __restrict__ energy_m1)
 {
     extern __shared__ float tile[];
@@ -61,7 +68,7 @@ k_kw_cells(KwConfig K, SectionGeom G, int sec0, int cells_stride, double* __rest
     const int lo = threadIdx.x * cell;
     if (lo >= cnt) return;
     const int len = min(cell, cnt - lo);
-    const long long slot = ((long long)(sec0 + sec) * cells_stride + ci);
+    const long long slot = ((long long)sec * cells_stride + ci);
     double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v;
     if (PASS == 1) {
         s1 = state[slot * 4 + 0]; s2 = state[slot * 4 + 1]; h1 = state[slot * 4 + 2]; h2 = state[slot * 4 + 3];
@@ -76,7 +83,7 @@ k_kw_cells(KwConfig K, SectionGeom G, int sec0, int cells_stride, double* __rest
         state[slot * 4 + 0] = s1; state[slot * 4 + 1] = s2; state[slot * 4 + 2] = h1; state[slot * 4 + 3] = h2;
     } else {
         energy[slot] = e;
-        if ((long long)ci * cell + len == n) energy_m1[sec0 + sec] = e_prev;
+        if ((long long)ci * cell + len == n) energy_m1[sec] = e_prev;
     }
 }
 
@@ -87,9 +94,8 @@ __device__ __forceinline__ void mat4_apply_add(const double* __restrict__ Mx, co
         s[r] += Mx[r * 4 + 0] * t[0] + Mx[r * 4 + 1] * t[1] + Mx[r * 4 + 2] * t[2] + Mx[r * 4 + 3] * t[3];
 }
 
-// One warp per section: turns zero-state end states into carry-in states, in place.
-__global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int sec0, int cells_stride,
-                          double* __restrict__ state)
+// One warp per union section: turns zero-state end states into carry-in states, in place.
+__global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int cells_stride, double* __restrict__ state)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -98,7 +104,7 @@ __global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int sec0, int cel
     int n;
     section_bounds(G, warp, start, n);
     const int ncells = (n + K.cell - 1) / K.cell;
-    double* st = state + (long long)(sec0 + warp) * cells_stride * 4;
+    double* st = state + (long long)warp * cells_stride * 4;
     double prev[4] = {0, 0, 0, 0};                           // state at the start of this group of 32 cells
     for (int g0 = 0; g0 < ncells; g0 += 32) {
         const int i = g0 + lane;
@@ -124,19 +130,54 @@ __global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int sec0, int cel
     }
 }
 
-// One warp per section: gating + gain.  lib.rs:142-214.
-__global__ void k_kw_gate(KwConfig K, SectionGeom G, int nsec, int sec0, int cells_stride,
-                          const double* __restrict__ energy, const double* __restrict__ energy_m1,
-                          double* __restrict__ lufs_out, double* __restrict__ gain_out, int out_stride)
+// One thread per (chunk, group) whose section starts later than the union's: re-filter the first
+// patch_cells cells of the group's section from zero state.  patch[(ci*G + g) * patch_cells + k].
+__global__ void k_kw_patch(KwConfig K, SectionGeom Gu, const SectionGeom* __restrict__ geoms, int nsec, int G,
+                           double* __restrict__ patch)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsec * G) return;
+    const int ci = t / G, g = t % G;
+    long long su, sg;
+    int nu, ng;
+    section_bounds(Gu, ci, su, nu);
+    section_bounds(geoms[g], ci, sg, ng);
+    if (sg <= su || ng <= 0) return;                          // same start as the union: nothing to patch
+    const float* __restrict__ x = geoms[g].audio + (sg - geoms[g].base);
+    double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v;
+    double* out = patch + (long long)t * K.patch_cells;
+    int pos = 0;
+    for (int k = 0; k < K.patch_cells; ++k) {
+        double e = 0;
+        const int end = min(pos + K.cell, ng);
+        for (; pos < end; ++pos) {
+            kw_step(K.cf, (double)x[pos], s1, s2, h1, h2, v);
+            e += v * v;
+        }
+        out[k] = e;
+    }
+}
+
+// One warp per (chunk, group): gating + gain.  lib.rs:142-214.
+__global__ void k_kw_gate(KwConfig K, SectionGeom Gu, const SectionGeom* __restrict__ geoms, int nsec, int G,
+                          int cells_stride, const double* __restrict__ energy, const double* __restrict__ energy_m1,
+                          const double* __restrict__ patch, double* __restrict__ lufs_out,
+                          double* __restrict__ gain_out)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= nsec) return;
-    long long start;
-    int n;
-    section_bounds(G, warp, start, n);
-    const double* E = energy + (long long)(sec0 + warp) * cells_stride;
+    if (warp >= nsec * G) return;
+    const int ci = warp / G, g = warp % G;
+    long long su, start;
+    int nu, n;
+    section_bounds(Gu, ci, su, nu);
+    section_bounds(geoms[g], ci, start, n);
     const int cell = K.cell;
+    const int i0 = (int)((start - su) / cell);                // first union cell of this group's section
+    const int npatch = start > su ? K.patch_cells : 0;
+    const double* Eu = energy + (long long)ci * cells_stride + i0;
+    const double* Ep = patch + (long long)warp * K.patch_cells;
+    auto E = [&](int c) { return c < npatch ? Ep[c] : Eu[c]; };
     const int ncells = (n + cell - 1) / cell;
     const double rate = (double)K.rate;
     const double NEG_INF = -INFINITY;
@@ -149,13 +190,13 @@ __global__ void k_kw_gate(KwConfig K, SectionGeom G, int nsec, int sec0, int cel
             long long u = (long long)win;
             if (u > n) u = n;
             double tot = 0;
-            for (int i = lane; i < ncells; i += 32) tot += E[i];
+            for (int i = lane; i < ncells; i += 32) tot += E(i);
             tot = warp_sum(tot);
             if (u == (long long)n - 1) {
                 // drop the last sample: replace the last cell's energy by the one without it
                 tot = 0;
-                for (int i = lane; i < ncells - 1; i += 32) tot += E[i];
-                tot = warp_sum(tot) + energy_m1[sec0 + warp];
+                for (int i = lane; i < ncells - 1; i += 32) tot += E(i);
+                tot = warp_sum(tot) + energy_m1[ci];
             }
             // lib.rs:149-157 (num_blocks = round(0) + 1 = 1) then the two gates on one block
             if (u > 0) {
@@ -172,7 +213,7 @@ __global__ void k_kw_gate(KwConfig K, SectionGeom G, int nsec, int sec0, int cel
             const int hop = cell * K.k_per_hop, win = 4 * hop;
             if (nb <= 0) {
                 double tot = 0;
-                for (int i = lane; i < ncells; i += 32) tot += E[i];
+                for (int i = lane; i < ncells; i += 32) tot += E(i);
                 tot = warp_sum(tot);
                 const double ms = tot / (double)n;
                 lufs = ms <= 0.0 ? NEG_INF : -0.691 + 10.0 * log10(ms);
@@ -189,7 +230,7 @@ __global__ void k_kw_gate(KwConfig K, SectionGeom G, int nsec, int sec0, int cel
                         const int c0 = (int)(j * K.k_per_hop);
                         const int c1 = min(c0 + 4 * K.k_per_hop, ncells);
                         double e = 0;
-                        for (int c = c0; c < c1; ++c) e += E[c];
+                        for (int c = c0; c < c1; ++c) e += E(c);
                         const double ms = e / (double)(u - l);
                         if (!(ms > 0.0)) continue;
                         const double ld = -0.691 + 10.0 * log10(ms);
@@ -207,8 +248,8 @@ __global__ void k_kw_gate(KwConfig K, SectionGeom G, int nsec, int sec0, int cel
         }
     }
     if (lane == 0) {
-        lufs_out[(long long)warp * out_stride] = lufs;
-        gain_out[(long long)warp * out_stride] = pow(10.0, (kTargetLufs - lufs) / 20.0);   // lib.rs:221-222
+        lufs_out[warp] = lufs;
+        gain_out[warp] = pow(10.0, (kTargetLufs - lufs) / 20.0);   // lib.rs:221-222
     }
 }
 
@@ -254,6 +295,13 @@ bool kw_config_create(int sample_rate, KwConfig* out, std::string* err)
     while (k <= hop && !(hop % k == 0 && hop / k <= 128)) ++k;
     K.k_per_hop = k;
     K.cell = hop / k;
+    {
+        // memory of the slowest K-weighting pole (the 38 Hz high-pass, a double pole of radius sqrt(a2))
+        const double r = sqrt(fabs(K.cf[11]));
+        int n = 1;
+        while ((double)(n + 1) * (double)(n + 1) * pow(r, (double)n) > 1e-20 && n < 10000000) ++n;
+        K.patch_cells = (n + K.cell - 1) / K.cell + 1;
+    }
     // Mc = A^cell by running the zero-input response of the 4 unit states for `cell` samples
     double Mc[16];
     for (int col = 0; col < 4; ++col) {
@@ -296,9 +344,9 @@ void kw_config_destroy(KwConfig* K)
     K->mpow = nullptr;
 }
 
-void launch_loudness(const KwConfig& K, const SectionGeom& G, int nsec, int sec0, int cells_stride,
-                     double* state, double* energy, double* energy_m1, double* lufs, double* gain,
-                     int out_stride, cudaStream_t st)
+void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom* h_geoms,
+                     const SectionGeom* d_geoms, int G, int nsec, int cells_stride, double* state, double* energy,
+                     double* energy_m1, double* patch, double* lufs, double* gain, cudaStream_t st)
 {
     if (nsec <= 0) return;
     static bool attr = false;
@@ -313,17 +361,20 @@ void launch_loudness(const KwConfig& K, const SectionGeom& G, int nsec, int sec0
     int nmax = 0;
     for (int s = 0; s < nsec; ++s) {
         int n;
-        section_bounds(G, s, start, n);
+        section_bounds(Gu, s, start, n);
         nmax = n > nmax ? n : nmax;
     }
     if (nmax <= 0) nmax = 1;
+    bool need_patch = false;
+    for (int g = 0; g < G; ++g) need_patch |= h_geoms[g].halo != Gu.halo;
     const int ncells = (nmax + K.cell - 1) / K.cell;
     dim3 grid((ncells + 127) / 128, nsec);
-    const int wblocks = (nsec * 32 + 127) / 128;
-    k_kw_cells<0><<<grid, 128, smem, st>>>(K, G, sec0, cells_stride, state, energy, energy_m1);
-    k_kw_scan<<<wblocks, 128, 0, st>>>(K, G, nsec, sec0, cells_stride, state);
-    k_kw_cells<1><<<grid, 128, smem, st>>>(K, G, sec0, cells_stride, state, energy, energy_m1);
-    k_kw_gate<<<wblocks, 128, 0, st>>>(K, G, nsec, sec0, cells_stride, energy, energy_m1, lufs, gain, out_stride);
+    k_kw_cells<0><<<grid, 128, smem, st>>>(K, Gu, cells_stride, state, energy, energy_m1);
+    k_kw_scan<<<(nsec * 32 + 127) / 128, 128, 0, st>>>(K, Gu, nsec, cells_stride, state);
+    k_kw_cells<1><<<grid, 128, smem, st>>>(K, Gu, cells_stride, state, energy, energy_m1);
+    if (need_patch) k_kw_patch<<<(nsec * G + 63) / 64, 64, 0, st>>>(K, Gu, d_geoms, nsec, G, patch);
+    k_kw_gate<<<(nsec * G * 32 + 127) / 128, 128, 0, st>>>(K, Gu, d_geoms, nsec, G, cells_stride, energy, energy_m1,
+                                                          patch, lufs, gain);
 }
 
 }  // namespace apd

@@ -12,17 +12,18 @@ struct KwConfig {
     int rate;
     int cell;             // samples per scan cell (divides the 100 ms hop)
     int k_per_hop;        // cells per hop
+    int patch_cells;      // cells after which the filters have forgotten their start state (see k_kw_patch)
     const double* mpow;   // device: Mc^1 .. Mc^32 (4x4 row-major each), Mc = state transition over one cell
 };
 
 bool kw_config_create(int sample_rate, KwConfig* out, std::string* err);
 void kw_config_destroy(KwConfig* K);
 
-// Loudness of sections 0..nsec-1 of geometry G.  Workspace rows are indexed sec0 + s:
-// state[(sec0+s) * cells_stride * 4], energy[(sec0+s) * cells_stride], energy_m1[sec0+s].
-// Results: lufs[s * out_stride], gain[s * out_stride].
-void launch_loudness(const KwConfig& K, const SectionGeom& G, int nsec, int sec0, int cells_stride,
-                     double* state, double* energy, double* energy_m1, double* lufs, double* gain,
-                     int out_stride, cudaStream_t st);
+// Loudness of every (chunk ci < nsec, group g < G) section.  Gu is the union geometry (largest halo);
+// h_geoms / d_geoms are the per-group geometries on host / device.  Workspace: state[nsec*cells_stride*4],
+// energy[nsec*cells_stride], energy_m1[nsec], patch[nsec*G*patch_cells].  Results: lufs/gain[ci*G + g].
+void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom* h_geoms,
+                     const SectionGeom* d_geoms, int G, int nsec, int cells_stride, double* state, double* energy,
+                     double* energy_m1, double* patch, double* lufs, double* gain, cudaStream_t st);
 
 }  // namespace apd
