@@ -229,7 +229,9 @@ struct apd_ctx {
     apd_candidate* d_out = nullptr;
     int out_capacity = 0;
     // tone
-    int tone_ctas = 0, tone_wl = 0, tone_item_cap = 0;
+    int tone_ctas = 0, tone_wl = 0, tone_item_cap = 0;      // tone_ctas: work items per tone round
+    int tone_max_P = 0, tone_max_L = 0;
+    double* d_tone_stats = nullptr;
     long long tone_stride = 0;
     double2* d_tone_scratch = nullptr;
     void* d_tone_items = nullptr;
@@ -600,6 +602,10 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         const long long per_cta = 3LL * 2 * max_P * (long long)sizeof(double2);
         c->tone_ctas = (int)std::max<long long>(1, std::min<long long>(64, (1LL << 31) / per_cta));
         CK(dalloc(&c->d_tone_scratch, (size_t)c->tone_ctas * 3 * 2 * max_P));
+        CK(dalloc(&c->d_tone_stats, (size_t)c->tone_ctas * 3 * 4));
+        c->tone_max_P = max_P;
+        for (auto& cl : c->clips)
+            if (cl.tone_P > 0) c->tone_max_L = std::max(c->tone_max_L, cl.L);
         c->tone_item_cap = std::max(4096, B * n_clips);
         CK(cudaMalloc(&c->d_tone_items, tone_item_bytes() * c->tone_item_cap));
         CK(dalloc(&c->d_tone_metrics, (size_t)c->tone_item_cap * 15));
@@ -632,7 +638,7 @@ extern "C" int apd_destroy(apd_ctx* c)
                     c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
                     c->d_gain, c->d_spec, c->d_scratch, c->d_unit_max, c->d_unit_npeaks, c->d_counts, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
-                    c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics};
+                    c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics, c->d_tone_stats};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(c->h_geoms);
     cudaFreeHost(c->h_counts);
@@ -766,9 +772,9 @@ static void phase2_round(apd_ctx* c, int slot0, cudaStream_t st)
     ++c->launches;
 }
 
-static void phase2_tone(apd_ctx* c, cudaStream_t st)
+static void phase2_tone(apd_ctx* c, int n_items, cudaStream_t st)
 {
-    if (c->tone_ctas <= 0) return;
+    if (c->tone_ctas <= 0 || n_items <= 0) return;
     const int S = (int)c->shapes.size(), G = (int)c->groups.size();
     PeakArgs PA{c->d_sel, c->d_counts + S, 0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
                 c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
@@ -778,8 +784,8 @@ static void phase2_tone(apd_ctx* c, cudaStream_t st)
                   c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs, c->d_tone_pre_ptrs, c->d_tone_post_ptrs};
     VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + S + 1, c->out_capacity,
                   c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
-    launch_tone_batch(VA, c->d_tone_items, c->d_counts + S + 3, c->tone_item_cap, c->d_tone_metrics,
-                      c->tone_ctas, c->tone_wl, st, &c->launches);
+    launch_tone_batch(VA, c->d_tone_items, c->d_counts + S + 3, n_items, c->d_tone_metrics, c->d_tone_stats,
+                      c->tone_ctas, c->tone_max_P, c->tone_max_L, c->tone_wl, st, &c->launches);
 }
 
 // Select the units that can have peaks, then run the first phase-2 round without waiting for the
@@ -834,10 +840,15 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
                    double* lufs_host, cudaStream_t st)
 {
     const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size(), S = (int)c->shapes.size();
-    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int slot0 = c->n_slots; slot0 < c->h_counts[S]; slot0 += c->n_slots) phase2_round(c, slot0, st);
-    phase2_tone(c, st);
+    if (c->h_counts[S] > c->n_slots) {
+        for (int slot0 = c->n_slots; slot0 < c->h_counts[S]; slot0 += c->n_slots) phase2_round(c, slot0, st);
+        CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    phase2_tone(c, c->h_counts[S + 3], st);
+    if (c->profile) cudaEventRecord(c->ev[4], st);
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int n = c->h_counts[S + 1];
@@ -902,7 +913,6 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
     if ((rc = stage_correlate_max(c, st))) return rc;
     if (prof) cudaEventRecord(c->ev[3], st);
     if ((rc = stage_peaks_verify(c, st))) return rc;
-    if (prof) cudaEventRecord(c->ev[4], st);
     rc = collect(c, cand_host, cap, n_cand, trace, lufs_host, st);
     if (prof && rc == APD_OK) {
         for (int i = 0; i < 4; ++i) {

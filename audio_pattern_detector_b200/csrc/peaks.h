@@ -63,7 +63,7 @@ struct VerifyArgs {
     int* out_count;
     int out_capacity;
     apd_candidate* slot_cands;    // [slot][peak_stride] scratch records
-    double2* tone_scratch;        // per (slot-candidate) Bluestein buffers
+    double2* tone_scratch;        // [round item][segment][2] Bluestein ping-pong buffers
     long long tone_scratch_stride;
     int tone_scratch_slots;
 };
@@ -73,8 +73,9 @@ constexpr int kMaxSlots = 1024;           // slots per phase-2 round (k_emit kee
 void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches);
 void launch_tone_collect(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
                          cudaStream_t st, long long* launches);
-void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items, int item_capacity, double* metrics,
-                       int tone_ctas, int wl, cudaStream_t st, long long* launches);
+void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n_items, double* metrics,
+                       double* stats, int round_items, int max_P, int max_L, int wl, cudaStream_t st,
+                       long long* launches);
 void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches);
 void launch_tone_tables(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* chirp_fft,
                         double2* pre, double2* post, cudaStream_t st);

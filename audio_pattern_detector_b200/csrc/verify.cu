@@ -7,6 +7,7 @@
 //    detection_utils.py:41-142 (Hann-windowed full-length spectrum and 25 ms STFT frames of the
 //    matched segment and both flanks, all float64).  The arbitrary-length DFT (L = 1223, 1827, ...)
 //    is evaluated exactly as a Bluestein chirp-z transform over a power-of-two float64 FFT.
+#include <algorithm>
 #include <cmath>
 
 #include "internal.h"
@@ -292,169 +293,291 @@ __global__ void k_tone_collect(VerifyArgs A, int nslots, ToneItem* items, int* n
     *n_items = cnt;
 }
 
-// metrics[item][seg][5]
-__global__ void __launch_bounds__(1024)
-k_tone_metrics(VerifyArgs A, const ToneItem* __restrict__ items, const int* __restrict__ n_items,
-               double* __restrict__ metrics)
+// ---------------------------------------------------------------------------
+// Tone metrics for a round of up to R work items x 3 segments, as whole-GPU kernels:
+//   prep -> forward FFT passes -> multiply by the chirp spectrum -> inverse FFT passes ->
+//   spectrum statistics -> STFT frame bins -> per-frame statistics -> run-length summary.
+// Each (item, segment) owns two double2 buffers A, B of `stride` elements (ping-pong).
+// ---------------------------------------------------------------------------
+struct ToneRound {
+    const ToneItem* items;
+    int i0, n_round;              // items [i0, i0 + n_round)
+    double2* scratch;
+    long long stride;
+    double* stats;                // [(r*3+seg)*4] = {tot, band sum, detected Hz, -}
+    double* metrics;              // [item][seg][5]
+    int wl, hop;
+};
+
+__device__ __forceinline__ double2* tone_buf(const ToneRound& T, int r, int seg, int which)
 {
-    extern __shared__ double2 ftw[];            // frame twiddles e^{-2 pi i t / wl}, then frame Hann (as .x)
+    return T.scratch + (((long long)r * 3 + seg) * 2 + which) * T.stride;
+}
+
+__device__ __forceinline__ int tone_npass(int P)      // radix-4 passes + one radix-2 pass if log2 P is odd
+{
+    const int lg = 31 - __clz(P);
+    return (lg >> 1) + (lg & 1);
+}
+
+struct ToneSeg {
+    const float* x;               // section start
+    int nsec, L, P, ms, clip;
+    double gain, f0;
+};
+
+__device__ __forceinline__ ToneSeg tone_seg(const VerifyArgs& A, const ToneItem& item, int seg)
+{
+    ToneSeg s;
+    s.clip = item.clip;
+    const int g = A.pk.clip_group[item.clip];
+    long long start;
+    section_bounds(A.pk.geom[g], item.ci, start, s.nsec);
+    s.x = A.pk.geom[g].audio + (start - A.pk.geom[g].base);
+    s.gain = A.gains[(long long)item.ci * A.n_groups + g];
+    s.L = A.pk.clip_len[item.clip];
+    s.P = A.cv.tone_P[item.clip];
+    s.f0 = A.cv.tone_hz[item.clip];
+    s.ms = item.peak - s.L + 1 + (seg == 1 ? -s.L : (seg == 2 ? s.L : 0));       // apd.py:650-653
+    return s;
+}
+
+__device__ __forceinline__ double tone_sample(const ToneSeg& s, int k)
+{
+    return (k >= 0 && k < s.nsec) ? (double)normalize_sample(s.x[k], s.gain) : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+k_tone_prep(VerifyArgs A, ToneRound T)
+{
+    const int r = blockIdx.z, seg = blockIdx.y;
+    if (r >= T.n_round) return;
+    const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= s.P) return;
+    double2 v = make_double2(0, 0);
+    if (n < s.L) {
+        const double xv = tone_sample(s, s.ms + n);
+        const double2 c = A.cv.tone_pre[s.clip][n];                 // hann * e^{-i pi n^2 / L}
+        v = make_double2(xv * c.x, xv * c.y);
+    }
+    tone_buf(T, r, seg, 0)[n] = v;
+}
+
+// One pass slot of the batched float64 FFT (see fft64 for the single-CTA variant used at init).
+template <bool INV>
+__global__ void __launch_bounds__(256)
+k_tone_fft_pass(VerifyArgs A, ToneRound T, int slot)
+{
+    const int r = blockIdx.z, seg = blockIdx.y;
+    if (r >= T.n_round) return;
+    const int clip = T.items[T.i0 + r].clip;
+    const int P = A.cv.tone_P[clip];
+    const int lg = 31 - __clz(P);
+    const int r4 = lg >> 1, np = r4 + (lg & 1);
+    if (slot >= np) return;
+    const int start_b = INV ? (np & 1) : 0;                        // the inverse starts where the forward ended
+    const double2* __restrict__ x = tone_buf(T, r, seg, (start_b + slot) & 1);
+    double2* __restrict__ y = tone_buf(T, r, seg, (start_b + slot + 1) & 1);
+    const double2* __restrict__ tw = A.cv.tone_tw[clip];
+    const int half = P >> 1, quarter = P >> 2;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < r4) {
+        if (j >= quarter) return;
+        const int Ns = 1 << (2 * slot);
+        const int tstep = P / (4 * Ns);
+        const int k = j & (Ns - 1);
+        const double2 a0 = x[j];
+        double2 a1 = x[j + quarter], a2 = x[j + 2 * quarter], a3 = x[j + 3 * quarter];
+        if (Ns > 1) {
+            a1 = zmul(a1, tw_at(tw, k * tstep, half, INV));
+            a2 = zmul(a2, tw_at(tw, 2 * k * tstep, half, INV));
+            a3 = zmul(a3, tw_at(tw, 3 * k * tstep, half, INV));
+        }
+        const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
+        const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
+        const double2 rr = INV ? make_double2(-d13.y, d13.x) : make_double2(d13.y, -d13.x);
+        const int o = (j / Ns) * 4 * Ns + k;
+        y[o] = make_double2(s02.x + s13.x, s02.y + s13.y);
+        y[o + Ns] = make_double2(d02.x + rr.x, d02.y + rr.y);
+        y[o + 2 * Ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
+        y[o + 3 * Ns] = make_double2(d02.x - rr.x, d02.y - rr.y);
+    } else {                                                        // the single radix-2 pass (Ns = P/2)
+        for (int jj = j; jj < half; jj += quarter) {
+            const double2 a = x[jj];
+            const double2 b = zmul(x[jj + half], tw_at(tw, jj, half, INV));
+            y[jj] = make_double2(a.x + b.x, a.y + b.y);
+            y[jj + half] = make_double2(a.x - b.x, a.y - b.y);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_tone_mul(VerifyArgs A, ToneRound T)
+{
+    const int r = blockIdx.z, seg = blockIdx.y;
+    if (r >= T.n_round) return;
+    const int clip = T.items[T.i0 + r].clip;
+    const int P = A.cv.tone_P[clip];
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P) return;
+    double2* f = tone_buf(T, r, seg, tone_npass(P) & 1);
+    f[n] = zmul(f[n], A.cv.tone_chirp_fft[clip][n]);
+}
+
+// One CTA per (segment, item): X_k = post[k] * conv[k] / P for k <= L/2 (conv ends in buffer A).
+__global__ void __launch_bounds__(1024)
+k_tone_stats(VerifyArgs A, ToneRound T)
+{
     __shared__ double red[32];
     __shared__ int s_arg;
-    const int seg = blockIdx.x;                 // 0 match, 1 left flank, 2 right flank
-    double2* buf0 = A.tone_scratch + ((long long)blockIdx.y * 3 + seg) * 2 * A.tone_scratch_stride;
-    double2* buf1 = buf0 + A.tone_scratch_stride;
-    const int sr = A.sample_rate;
-    double wlr = rint(0.025 * (double)sr);                                   // du.py:77 (banker's round)
-    const int wl = wlr > 32.0 ? (int)wlr : 32;
-    const int hop = wl / 2 > 1 ? wl / 2 : 1;
+    const int r = blockIdx.y, seg = blockIdx.x;
+    if (r >= T.n_round) return;
+    const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
+    const double2* __restrict__ c = tone_buf(T, r, seg, 0);
+    const double2* __restrict__ post = A.cv.tone_post[s.clip];
+    const double band = fmax(40.0, s.f0 * 0.08);                               // du.py:56
+    const double d = __ddiv_rn(1.0, (double)A.sample_rate);
+    const double fval = __ddiv_rn(1.0, __dmul_rn((double)s.L, d));            // np.fft.rfftfreq
+    const int nb = s.L / 2 + 1;
+    const double invP = 1.0 / (double)s.P;
+    double tot = 0, bsum = 0, best = -1.0;
+    int arg = 0x7fffffff;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+        const double2 z = zmul(c[k], post[k]);
+        const double re = z.x * invP, im = z.y * invP;
+        const double m2 = re * re + im * im;
+        tot += m2;
+        if (fabs(__dmul_rn((double)k, fval) - s.f0) <= band) bsum += m2;      // du.py:74
+        if (m2 > best) { best = m2; arg = k; }
+    }
+    tot = block_sum(tot, red);
+    bsum = block_sum(bsum, red);
+    double bm = best;                                                         // np.argmax: first maximum
+    for (int o2 = 16; o2 > 0; o2 >>= 1) bm = fmax(bm, __shfl_xor_sync(0xffffffffu, bm, o2));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bm;
+    if (threadIdx.x == 0) s_arg = 0x7fffffff;
+    __syncthreads();
+    double gm = -1.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) gm = fmax(gm, red[i]);
+    if (best == gm && arg != 0x7fffffff) atomicMin(&s_arg, arg);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int argk = s_arg == 0x7fffffff ? 0 : s_arg;
+        double* st = T.stats + ((long long)r * 3 + seg) * 4;
+        st[0] = tot;
+        st[1] = bsum;
+        st[2] = __dmul_rn((double)argk, fval);                                // du.py:62
+    }
+}
+
+// STFT frame bins (du.py:77-100): thread = (frame, bin) of one (item, segment); |X|^2 into buffer B.
+__global__ void __launch_bounds__(256)
+k_tone_frames(VerifyArgs A, ToneRound T)
+{
+    extern __shared__ double2 ftw[];            // e^{-2 pi i t / wl} (t < wl), then the frame Hann window (.x)
+    const int r = blockIdx.z, seg = blockIdx.y;
+    if (r >= T.n_round) return;
+    if (T.stats[((long long)r * 3 + seg) * 4] == 0.0) return;                 // du.py:65-72
+    const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
+    const int wl = T.wl, hop = T.hop;
+    const int nf = s.L - wl > 0 ? (s.L - wl + hop - 1) / hop : 0;             // range(0, L - wl, hop)
+    const int nbw = wl / 2 + 1;
+    const long long work = (long long)nf * nbw;
+    if ((long long)blockIdx.x * blockDim.x >= work) return;
     for (int t = threadIdx.x; t < wl; t += blockDim.x) {
-        double s, c;
-        sincospi(-2.0 * (double)t / (double)wl, &s, &c);
-        ftw[t] = make_double2(c, s);
-        const double h = wl > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(wl - 1)) : 1.0;
-        ftw[wl + t] = make_double2(h, 0.0);
+        double sn, cs;
+        sincospi(-2.0 * (double)t / (double)wl, &sn, &cs);
+        ftw[t] = make_double2(cs, sn);
+        ftw[wl + t] = make_double2(wl > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(wl - 1)) : 1.0, 0.0);
     }
     __syncthreads();
-    for (int it = blockIdx.y; it < *n_items; it += gridDim.y) {
-        const ToneItem item = items[it];
-        const int clip = item.clip;
-        const int g = A.pk.clip_group[clip];
-        long long start;
-        int nsec;
-        section_bounds(A.pk.geom[g], item.ci, start, nsec);
-        const float* __restrict__ x = A.pk.geom[g].audio + (start - A.pk.geom[g].base);
-        const double gain = A.gains[(long long)item.ci * A.n_groups + g];
-        const int L = A.pk.clip_len[clip];
-        const int P = A.cv.tone_P[clip];
-        const double2* __restrict__ tw = A.cv.tone_tw[clip];
-        const double2* __restrict__ cf = A.cv.tone_chirp_fft[clip];
-        const double2* __restrict__ pre = A.cv.tone_pre[clip];
-        const double2* __restrict__ post = A.cv.tone_post[clip];
-        const double f0 = A.cv.tone_hz[clip];
-        const int ms = item.peak - L + 1 + (seg == 1 ? -L : (seg == 2 ? L : 0));    // apd.py:650-653
-        double* out = metrics + ((long long)it * 3 + seg) * 5;
-        const double band = fmax(40.0, f0 * 0.08), lock = fmax(20.0, f0 * 0.04);   // du.py:56-57
-        const double d = __ddiv_rn(1.0, (double)sr);
-        const double fval = __ddiv_rn(1.0, __dmul_rn((double)L, d));         // np.fft.rfftfreq
-        const double fvalw = __ddiv_rn(1.0, __dmul_rn((double)wl, d));
-
-        // ---- full-length Hann-windowed spectrum via Bluestein
-        for (int n = threadIdx.x; n < P; n += blockDim.x) {
-            double2 v = make_double2(0, 0);
-            if (n < L) {
-                const int k = ms + n;
-                const double xv = (k >= 0 && k < nsec) ? (double)normalize_sample(x[k], gain) : 0.0;
-                const double2 c = pre[n];
-                v = make_double2(xv * c.x, xv * c.y);
-            }
-            buf0[n] = v;
-        }
-        __syncthreads();
-        double2* r = fft64<false>(buf0, buf1, tw, P);
-        double2* o = r == buf0 ? buf1 : buf0;
-        for (int n = threadIdx.x; n < P; n += blockDim.x) r[n] = zmul(r[n], cf[n]);
-        __syncthreads();
-        double2* c = fft64<true>(r, o, tw, P);
-        const int nb = L / 2 + 1;
-        const double invP = 1.0 / (double)P;
-        double tot = 0, bsum = 0, best = -1.0;
-        int arg = 0x7fffffff;
-        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-            const double2 z = zmul(c[k], post[k]);
-            const double re = z.x * invP, im = z.y * invP;
-            const double m2 = re * re + im * im;
-            tot += m2;
-            if (fabs(__dmul_rn((double)k, fval) - f0) <= band) bsum += m2;    // du.py:74
-            if (m2 > best) { best = m2; arg = k; }
-        }
-        tot = block_sum(tot, red);
-        bsum = block_sum(bsum, red);
-        // argmax, first maximum wins (np.argmax)
-        {
-            double bm = best;
-            for (int o2 = 16; o2 > 0; o2 >>= 1) bm = fmax(bm, __shfl_xor_sync(0xffffffffu, bm, o2));
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bm;
-            if (threadIdx.x == 0) s_arg = 0x7fffffff;
-            __syncthreads();
-            double gm = -1.0;
-            for (int i = 0; i < (blockDim.x >> 5); ++i) gm = fmax(gm, red[i]);
-            if (best == gm && arg != 0x7fffffff) atomicMin(&s_arg, arg);
-            __syncthreads();
-        }
-        const int argk = s_arg == 0x7fffffff ? 0 : s_arg;
-        const double detected = __dmul_rn((double)argk, fval);               // du.py:62
-
-        // ---- STFT frames (du.py:77-112): direct DFT of each Hann-windowed frame
-        const int nf = L - wl > 0 ? (L - wl + hop - 1) / hop : 0;             // range(0, L - wl, hop)
-        const int nbw = wl / 2 + 1;
-        __syncthreads();                                                      // conv buffer no longer needed
-        double* fm2 = (double*)buf0;                                          // [frame][bin] |X|^2
-        if (tot != 0.0) {
-            for (long long w = threadIdx.x; w < (long long)nf * nbw; w += blockDim.x) {
-                const int f = (int)(w / nbw), kb = (int)(w % nbw);
-                const int s0 = ms + f * hop;
-                double re = 0, im = 0;
-                int ph = 0;
-                for (int n = 0; n < wl; ++n) {
-                    const int k = s0 + n;
-                    const double xv = (k >= 0 && k < nsec) ? (double)normalize_sample(x[k], gain) : 0.0;
-                    const double xw = xv * ftw[wl + n].x;
-                    const double2 e = ftw[ph];
-                    re += xw * e.x;
-                    im += xw * e.y;
-                    ph += kb;
-                    if (ph >= wl) ph -= wl;
-                }
-                fm2[w] = re * re + im * im;
-            }
-        }
-        __syncthreads();
-        // per-frame reductions by single threads, then the run-length logic by thread 0
-        double* fpur = (double*)buf1;              // [frame] purity (or -1 = zero-energy frame)
-        unsigned char* fact = (unsigned char*)(fpur + nf);
-        if (tot != 0.0) {
-            for (int f = threadIdx.x; f < nf; f += blockDim.x) {
-                double e = 0, bs = 0, bm = -1.0;
-                int ak = 0;
-                for (int kb = 0; kb < nbw; ++kb) {
-                    const double m2 = fm2[(long long)f * nbw + kb];
-                    e += m2;
-                    if (fabs(__dmul_rn((double)kb, fvalw) - f0) <= band) bs += m2;
-                    if (m2 > bm) { bm = m2; ak = kb; }
-                }
-                if (e == 0.0) { fpur[f] = -1.0; fact[f] = 0; continue; }
-                const double fdom = __dmul_rn((double)ak, fvalw);
-                const double pur = bs / e;
-                const double tol = fmax(1e-9 * fmax(fabs(fdom), fabs(f0)), lock);    // math.isclose
-                fpur[f] = pur;
-                fact[f] = (fabs(fdom - f0) <= tol && pur >= 0.55) ? 1 : 0;           // du.py:102-105
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double ratio = 0, meanp = 0;
-            int longest = 0;
-            if (tot != 0.0) {
-                int frames = 0, active = 0, run = 0;
-                double psum = 0;
-                for (int f = 0; f < nf; ++f) {
-                    if (fpur[f] < 0.0) { run = 0; continue; }
-                    ++frames;
-                    if (fact[f]) { ++active; ++run; longest = run > longest ? run : longest; psum += fpur[f]; }
-                    else run = 0;
-                }
-                ratio = frames > 0 ? (double)active / (double)frames : 0.0;
-                meanp = active > 0 ? psum / (double)active : 0.0;
-            }
-            out[0] = detected;
-            out[1] = tot != 0.0 ? bsum / tot : 0.0;                           // du.py:64-75
-            out[2] = ratio;
-            out[3] = (double)longest;
-            out[4] = meanp;
-        }
-        __syncthreads();
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= work) return;
+    const int f = (int)(w / nbw), kb = (int)(w % nbw);
+    const int s0 = s.ms + f * hop;
+    double re = 0, im = 0;
+    int ph = 0;
+    for (int n = 0; n < wl; ++n) {
+        const double xw = tone_sample(s, s0 + n) * ftw[wl + n].x;
+        const double2 e = ftw[ph];
+        re += xw * e.x;
+        im += xw * e.y;
+        ph += kb;
+        if (ph >= wl) ph -= wl;
     }
+    ((double*)tone_buf(T, r, seg, 1))[w] = re * re + im * im;
+}
+
+// Thread per frame: energy, dominant bin, band purity, "active" flag (du.py:89-105) into buffer A.
+__global__ void __launch_bounds__(128)
+k_tone_frame_stats(VerifyArgs A, ToneRound T)
+{
+    const int r = blockIdx.z, seg = blockIdx.y;
+    if (r >= T.n_round) return;
+    if (T.stats[((long long)r * 3 + seg) * 4] == 0.0) return;
+    const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
+    const int wl = T.wl, hop = T.hop;
+    const int nf = s.L - wl > 0 ? (s.L - wl + hop - 1) / hop : 0;
+    const int nbw = wl / 2 + 1;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const double* __restrict__ fm2 = (const double*)tone_buf(T, r, seg, 1);
+    double* fpur = (double*)tone_buf(T, r, seg, 0);
+    unsigned char* fact = (unsigned char*)(fpur + nf);
+    const double band = fmax(40.0, s.f0 * 0.08), lock = fmax(20.0, s.f0 * 0.04);   // du.py:56-57
+    const double d = __ddiv_rn(1.0, (double)A.sample_rate);
+    const double fvalw = __ddiv_rn(1.0, __dmul_rn((double)wl, d));
+    double e = 0, bs = 0, bm = -1.0;
+    int ak = 0;
+    for (int kb = 0; kb < nbw; ++kb) {
+        const double m2 = fm2[(long long)f * nbw + kb];
+        e += m2;
+        if (fabs(__dmul_rn((double)kb, fvalw) - s.f0) <= band) bs += m2;
+        if (m2 > bm) { bm = m2; ak = kb; }
+    }
+    if (e == 0.0) { fpur[f] = -1.0; fact[f] = 0; return; }
+    const double fdom = __dmul_rn((double)ak, fvalw);
+    const double pur = bs / e;
+    const double tol = fmax(1e-9 * fmax(fabs(fdom), fabs(s.f0)), lock);       // math.isclose(abs_tol=lock)
+    fpur[f] = pur;
+    fact[f] = (fabs(fdom - s.f0) <= tol && pur >= 0.55) ? 1 : 0;              // du.py:102-105
+}
+
+// Thread per (item, segment): run-length summary over frames (du.py:106-117) and the 5 metrics.
+__global__ void k_tone_final(VerifyArgs A, ToneRound T)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T.n_round * 3) return;
+    const int r = t / 3, seg = t % 3;
+    const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
+    const double* st = T.stats + (long long)t * 4;
+    const double tot = st[0];
+    const int wl = T.wl, hop = T.hop;
+    const int nf = s.L - wl > 0 ? (s.L - wl + hop - 1) / hop : 0;
+    const double* fpur = (const double*)tone_buf(T, r, seg, 0);
+    const unsigned char* fact = (const unsigned char*)(fpur + nf);
+    double ratio = 0, meanp = 0;
+    int longest = 0;
+    if (tot != 0.0) {
+        int frames = 0, active = 0, run = 0;
+        double psum = 0;
+        for (int f = 0; f < nf; ++f) {
+            if (fpur[f] < 0.0) { run = 0; continue; }
+            ++frames;
+            if (fact[f]) { ++active; ++run; longest = run > longest ? run : longest; psum += fpur[f]; }
+            else run = 0;
+        }
+        ratio = frames > 0 ? (double)active / (double)frames : 0.0;
+        meanp = active > 0 ? psum / (double)active : 0.0;
+    }
+    double* out = T.metrics + ((long long)(T.i0 + r) * 3 + seg) * 5;
+    out[0] = st[2];
+    out[1] = tot != 0.0 ? st[1] / tot : 0.0;                                  // du.py:64-75
+    out[2] = ratio;
+    out[3] = (double)longest;
+    out[4] = meanp;
 }
 
 // Decision (apd.py:707-724) and record emission for the deferred tone candidates.
@@ -542,19 +665,42 @@ void launch_tone_collect(const VerifyArgs& A, int nslots, void* items, int* n_it
     ++*launches;
 }
 
-void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items, int item_capacity, double* metrics,
-                       int tone_ctas, int wl, cudaStream_t st, long long* launches)
+void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n_items, double* metrics,
+                       double* stats, int round_items, int max_P, int max_L, int wl, cudaStream_t st,
+                       long long* launches)
 {
-    if (tone_ctas <= 0) return;
+    if (n_items <= 0 || round_items <= 0) return;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_tone_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(k_tone_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr = true;
     }
-    dim3 g(3, tone_ctas);
-    k_tone_metrics<<<g, 1024, (size_t)2 * wl * sizeof(double2), st>>>(A, (const ToneItem*)items, n_items, metrics);
-    k_tone_decide<<<(item_capacity + 127) / 128, 128, 0, st>>>(A, (const ToneItem*)items, n_items, metrics);
-    *launches += 2;
+    int lg = 0;
+    while ((1 << lg) < max_P) ++lg;
+    const int max_pass = (lg >> 1) + (lg & 1);
+    const int hop = wl / 2 > 1 ? wl / 2 : 1;
+    const int nf_max = max_L - wl > 0 ? (max_L - wl + hop - 1) / hop : 0;
+    const long long work_max = (long long)nf_max * (wl / 2 + 1);
+    for (int i0 = 0; i0 < n_items; i0 += round_items) {
+        ToneRound T{(const ToneItem*)items, i0, std::min(round_items, n_items - i0), A.tone_scratch,
+                    A.tone_scratch_stride, stats, metrics, wl, hop};
+        const unsigned R = (unsigned)T.n_round;
+        k_tone_prep<<<dim3((max_P + 255) / 256, 3, R), 256, 0, st>>>(A, T);
+        for (int s = 0; s < max_pass; ++s)
+            k_tone_fft_pass<false><<<dim3((max_P / 4 + 255) / 256, 3, R), 256, 0, st>>>(A, T, s);
+        k_tone_mul<<<dim3((max_P + 255) / 256, 3, R), 256, 0, st>>>(A, T);
+        for (int s = 0; s < max_pass; ++s)
+            k_tone_fft_pass<true><<<dim3((max_P / 4 + 255) / 256, 3, R), 256, 0, st>>>(A, T, s);
+        k_tone_stats<<<dim3(3, R), 1024, 0, st>>>(A, T);
+        if (work_max > 0) {
+            k_tone_frames<<<dim3((unsigned)((work_max + 255) / 256), 3, R), 256, (size_t)2 * wl * sizeof(double2), st>>>(A, T);
+            k_tone_frame_stats<<<dim3((nf_max + 127) / 128, 3, R), 128, 0, st>>>(A, T);
+        }
+        k_tone_final<<<(T.n_round * 3 + 63) / 64, 64, 0, st>>>(A, T);
+        *launches += 5 + 2 * max_pass + (work_max > 0 ? 2 : 0);
+    }
+    k_tone_decide<<<(n_items + 127) / 128, 128, 0, st>>>(A, (const ToneItem*)items, n_items_dev, metrics);
+    ++*launches;
 }
 
 void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
