@@ -9,11 +9,10 @@
 // column kernels put q on the lanes (a warp covers 32..64-byte row segments of adjacent
 // columns).
 //
-// Exchange buffer layouts:
-//   column kernels : buf[e * TB + q]                      (q on lanes: conflict free)
-//   row kernels    : buf[q * PITCH + e + (e >> 3)]        (1 pad per 8 elements: the 8- and
-//                                                          64-element strides of radix-8 passes
-//                                                          fall on distinct banks)
+// Exchange buffer layouts (XOR swizzles found by exhaustive search over the three access
+// patterns of the 8*8*R passes; every LDS.64 / STS.64 of a half-warp hits 16 distinct 8-byte slots):
+//   row kernels    : buf[q * N + (e ^ ((e >> 3) & 15))]
+//   column kernels : buf[(e ^ ((e >> 3) & 1)) * TB + q]    (TB = 8 adjacent columns on the lanes)
 #pragma once
 #include "fft_sub.cuh"
 
@@ -59,27 +58,35 @@ __device__ __forceinline__ void unit_powers(float2 w, float2* p)
     for (int r = 2; r < R; ++r) p[r] = cmul(p[r >> 1], p[r - (r >> 1)]);
 }
 
-// One radix-R Stockham pass for butterfly j of a transform, split in two halves so a single
-// exchange buffer can be used (all loads of a pass complete before any store of that pass):
-//   bfly_load : v[r] = LD(j + r*T), inter-pass twiddle, R-point DFT   (results stay in registers)
-//   bfly_store: ST(j0 + r*NS, v[r])
-template <int R, int SIGN, int N, int NS, class LD>
-__device__ __forceinline__ void bfly_load(int j, const float2* __restrict__ tws, LD ld, float2* v)
+// One radix-R Stockham pass for butterfly j of a transform, in pieces so that (a) a single exchange
+// buffer can be used (all loads of a pass complete before any store of that pass) and (b) the
+// inter-pass twiddles w_{NS R}^{k r}, k = j mod NS, which depend only on the thread, can be computed
+// once per CTA and kept in registers while the CTA loops over many transforms:
+//   pass_twiddles : pw[r] = w^{k r}          (once)
+//   bfly_ld       : v[r] = LD(j + r*T)
+//   bfly_tw       : v[r] *= pw[r]
+//   Dft<R>::run   : R-point DFT in registers
+//   bfly_store    : ST(j0 + r*NS, v[r])
+template <int R, int SIGN, int NS>
+__device__ __forceinline__ void pass_twiddles(int j, float2* pw)
+{
+    const int k = j % NS;
+    unit_powers<R>(cispif((float)SIGN * 2.0f * (float)k * (1.0f / (float)(NS * R))), pw);
+}
+
+template <int R, int N, class LD>
+__device__ __forceinline__ void bfly_ld(int j, LD ld, float2* v)
 {
     constexpr int T = N / R;
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = ld(j + r * T);
-    if (NS > 1) {
-        const int k = j % NS;
-        constexpr int tstep = N / (NS * R);
+}
+
+template <int R>
+__device__ __forceinline__ void bfly_tw(float2* v, const float2* pw)
+{
 #pragma unroll
-        for (int r = 1; r < R; ++r) {
-            float2 w = tws[k * r * tstep];
-            if (SIGN > 0) w.y = -w.y;
-            v[r] = cmul(v[r], w);
-        }
-    }
-    Dft<R, SIGN>::run(v);
+    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], pw[r]);
 }
 
 template <int R, int NS, class ST>
@@ -90,10 +97,13 @@ __device__ __forceinline__ void bfly_store(int j, ST st, const float2* v)
     for (int r = 0; r < R; ++r) st(j0 + r * NS, v[r]);
 }
 
-__device__ __forceinline__ void fill_twiddles(float2* tws, int n)
+// t[r] = base * step^r, r < R (running product: R-1 complex multiplies)
+template <int R>
+__device__ __forceinline__ void geometric(float2 base, float2 step, float2* t)
 {
-    const float inv = 1.0f / (float)n;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) tws[t] = cispif(-2.0f * (float)t * inv);
+    t[0] = base;
+#pragma unroll
+    for (int r = 1; r < R; ++r) t[r] = cmul(t[r - 1], step);
 }
 
 }  // namespace apd
