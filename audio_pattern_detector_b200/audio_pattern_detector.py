@@ -309,11 +309,17 @@ class AudioPatternDetector:
 
     # ------------------------------------------------------------------ public scanning API
     def scan_array(self, audio: "NDArray[np.float32] | Any", on_pattern_detected: Optional[PatternDetectedCallback] = None,
-                   collect_trace: bool = False) -> ScanResult:
+                   collect_trace: bool = False, chunk_range: Optional[tuple[int, int]] = None,
+                   base_sample: int = 0, total_samples: Optional[int] = None) -> ScanResult:
         """Scan a whole in-memory stream (numpy array or CUDA float32 tensor).
 
         B200-side extension of the reference API: the stream is made device resident once and
-        scanned ``max_batch_chunks`` chunks per launch sequence."""
+        scanned ``max_batch_chunks`` chunks per launch sequence.
+
+        Sharded use (sharding.py): ``audio`` is a slab of a longer stream starting at stream sample
+        ``base_sample`` (it must contain the look-back halo of ``chunk_range[0]``), ``chunk_range``
+        the global chunk indices this call scans and ``total_samples`` the length of the whole
+        stream (only its final chunk is shorter)."""
         torch = _torch()
         if isinstance(audio, np.ndarray):
             dev = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(f"cuda:{self._device}")
@@ -321,22 +327,30 @@ class AudioPatternDetector:
             dev = audio.to(device=f"cuda:{self._device}", dtype=torch.float32, non_blocking=True).contiguous()
         n = dev.numel()
         C_ = self._chunk_samples
-        n_chunks = (n + C_ - 1) // C_
+        end_sample = base_sample + n                    # one past the last stream sample held
+        if total_samples is not None and total_samples < end_sample:
+            raise ValueError("total_samples is smaller than the slab")
+        n_chunks = (end_sample + C_ - 1) // C_
+        first, last = (0, n_chunks) if chunk_range is None else chunk_range
+        if not 0 <= first <= last <= n_chunks:
+            raise ValueError(f"chunk_range {chunk_range} outside the slab's chunks [0, {n_chunks})")
+        if total_samples is not None and last < n_chunks and last * C_ > end_sample:
+            raise ValueError("slab ends inside a chunk that is not the stream's last")
         peak_times: dict[str, list[float]] = {c.name: [] for c in self.audio_clips}
         events: list[tuple[float, str]] = []
         all_cands: list[Candidate] = []
         trace: Optional[dict] = {} if collect_trace else None
         with torch.cuda.device(self._device):
-            for c0 in range(0, n_chunks, self._max_batch):
-                c1 = min(n_chunks, c0 + self._max_batch)
-                cands, tr = self._scan_batch(dev.data_ptr(), 0, n, c0, c1, collect_trace)
+            for c0 in range(first, last, self._max_batch):
+                c1 = min(last, c0 + self._max_batch)
+                cands, tr = self._scan_batch(dev.data_ptr(), base_sample, n, c0, c1, collect_trace)
                 all_cands.extend(cands)
                 if trace is not None and tr:
                     trace.update(tr)
                 self._emit_batch(cands, c0, c1, peak_times, events, on_pattern_detected)
         total = 0.0
-        for i in range(n_chunks):                                           # reference :301
-            total += (min((i + 1) * C_, n) - i * C_) / self.target_sample_rate
+        for i in range(first, last):                                        # reference :301
+            total += (min((i + 1) * C_, end_sample) - i * C_) / self.target_sample_rate
         return ScanResult(peak_times=peak_times, events=events, candidates=all_cands, unit_trace=trace,
                           total_time=total)
 

@@ -208,6 +208,7 @@ struct apd_ctx {
     float2* d_spec = nullptr;
     long long scratch_elems = 0;
     float2* d_scratch = nullptr;
+    void* d_unit_desc = nullptr;          // per-unit descriptors of one inverse launch (corr_inv.cu)
     int inv_units = 0;                    // units per inverse launch
     unsigned int* d_unit_max = nullptr;
     int* d_unit_npeaks = nullptr;
@@ -285,6 +286,7 @@ struct InitTmp {
     const float2** spec_ptr = nullptr;    // [1]
     long long* zero_ll = nullptr;         // [1] = 0
     SectionGeom* geom = nullptr;          // [1]
+    void* desc = nullptr;                 // one unit descriptor
 };
 
 static int self_correlation(apd_ctx* c, ClipHost& cl, InitTmp& t)
@@ -311,11 +313,11 @@ static int self_correlation(apd_ctx* c, ClipHost& cl, InitTmp& t)
     const float2* hp = sb;
     CK(cudaMemcpy(t.spec_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(t.geom, &Ga, sizeof(Ga), cudaMemcpyHostToDevice));
-    UnitSrc U{nullptr, nullptr, t.ints, 1, 0};                // dense: unit 0 = (section 0, clip 0)
+    UnitSrc U{nullptr, nullptr, t.ints, 1, 0, 0};                // dense: unit 0 = (section 0, clip 0)
     UnitCtx X{t.geom, t.ints, t.ints + 1, t.zero_ll, t.spec_ptr};
     InvOut O{t.max_bits, 1, cl.d_self_corr, (long long)(2 * L - 1), t.zero_f};
-    launch_inverse(P, X, sa, P.M, U, 1, scr, O, false, 0);
-    launch_inverse(P, X, sa, P.M, U, 1, scr, O, true, 0);
+    launch_inverse(P, X, sa, P.M, U, 1, scr, t.desc, O, false, 0);
+    launch_inverse(P, X, sa, P.M, U, 1, scr, t.desc, O, true, 0);
     CK(cudaDeviceSynchronize());
     unsigned int bits = 0;
     CK(cudaMemcpy(&bits, t.max_bits, sizeof(bits), cudaMemcpyDeviceToHost));
@@ -418,6 +420,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(dalloc(&tmp.zero_ll, 1));
     CK(cudaMemset(tmp.zero_ll, 0, sizeof(long long)));
     CK(dalloc(&tmp.geom, 1));
+    CK(cudaMalloc(&tmp.desc, corr_inv_desc_bytes(1)));
     CK(dalloc(&d_tl, 1));
     CK(dalloc(&d_tg, 1));
     CK(dalloc(&d_tpatch, (size_t)c->kw.patch_cells));
@@ -550,7 +553,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(upload(&c->d_tone_pre_ptrs, h_pre));
     CK(upload(&c->d_tone_post_ptrs, h_post));
     cudaFree(tmp.max_bits); cudaFree(tmp.ints); cudaFree(tmp.zero_f); cudaFree((void*)tmp.spec_ptr);
-    cudaFree(tmp.zero_ll); cudaFree(tmp.geom);
+    cudaFree(tmp.zero_ll); cudaFree(tmp.geom); cudaFree(tmp.desc);
     cudaFree(d_tl); cudaFree(d_tg); cudaFree(d_tstate); cudaFree(d_ten); cudaFree(d_tem1); cudaFree(d_tpatch);
     {
         std::vector<long long> h_off(n_clips);
@@ -577,6 +580,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
     c->scratch_elems = std::max<long long>(std::max<long long>(B, c->inv_units), c->n_slots) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
+    CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(std::max(c->inv_units, c->n_slots))));
     CK(dalloc(&c->d_unit_max, (size_t)B * n_clips));
     CK(dalloc(&c->d_unit_npeaks, (size_t)B * n_clips));
     CK(dalloc(&c->d_counts, (size_t)S + 4));
@@ -638,7 +642,8 @@ extern "C" int apd_destroy(apd_ctx* c)
                     c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
                     c->d_gain, c->d_spec, c->d_scratch, c->d_unit_max, c->d_unit_npeaks, c->d_counts, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
-                    c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics, c->d_tone_stats};
+                    c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics, c->d_tone_stats,
+                    c->d_unit_desc};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(c->h_geoms);
     cudaFreeHost(c->h_counts);
@@ -727,14 +732,15 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
     const int B = c->chunk_end - c->chunk_begin;
     InvOut O{c->d_unit_max, c->n_clips, nullptr, 0, c->d_self_max};
     const UnitCtx X = unit_ctx(c);
+    static const bool clip_major = !(getenv("APD_B200_CHUNK_MAJOR") && atoi(getenv("APD_B200_CHUNK_MAJOR")));
     for (auto& sc : c->shapes) {
         const int ns = (int)sc.clips.size();
         const int nunits = B * ns;
         for (int u0 = 0; u0 < nunits; u0 += c->inv_units) {
-            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, u0};
+            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, u0, clip_major ? B : 0};
             launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, std::min(c->inv_units, nunits - u0),
-                           c->d_scratch, O, false, st);
-            c->launches += 2;
+                           c->d_scratch, c->d_unit_desc, O, false, st);
+            c->launches += 3;
         }
     }
     CK(cudaGetLastError());
@@ -749,9 +755,9 @@ static void phase2_round(apd_ctx* c, int slot0, cudaStream_t st)
     const UnitCtx X = unit_ctx(c);
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
     for (int s = 0; s < S; ++s) {
-        UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0};
-        launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch, O, true, st);
-        c->launches += 2;
+        UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0, 0};
+        launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch, c->d_unit_desc, O, true, st);
+        c->launches += 3;
     }
     PeakArgs PA{c->d_sel, c->d_counts + S, slot0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
                 c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
@@ -944,10 +950,10 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
     CK(dalloc(&d_rng, 2));
     CK(cudaMemcpyAsync(d_u, &u, sizeof(u), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_rng, rng, sizeof(rng), cudaMemcpyHostToDevice, st));
-    UnitSrc U{d_u, d_rng, nullptr, 0, 0};
+    UnitSrc U{d_u, d_rng, nullptr, 0, 0, 0};
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
-    launch_inverse(plan, unit_ctx(c), c->d_spec, c->spec_slab, U, 1, c->d_scratch, O, true, st);
-    c->launches += 2;
+    launch_inverse(plan, unit_ctx(c), c->d_spec, c->spec_slab, U, 1, c->d_scratch, c->d_unit_desc, O, true, st);
+    c->launches += 3;
     CK(cudaMemcpyAsync(out_host, c->d_corr, sizeof(float) * no, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_u);

@@ -1,0 +1,352 @@
+// K2 -- fused spectral multiply + inverse four-step FFT + |.| + per-unit max (or normalised write-out)
+// for the hot shapes M = N1 x 512, N1 in {512, 640}.
+//
+// Replaces abs(fft_correlation.fft_correlate_1d(section, clip, 'full')), max and the divide of
+// reference audio_pattern_detector.py:491-494 for a whole launch of (chunk x pattern) units.
+//
+//   k_unit_desc : one 32-byte descriptor per unit of the launch (spectrum row pointers, N_out, where the
+//                 unit's maximum lives, the divisor in write mode) so the hot kernels do no unit
+//                 bookkeeping of their own.
+//   k_corr_rows : rows c of  X[c][:] .* H[c][:]  ->  512-point inverse FFT  ->  four-step twiddle  -> W[c][:]
+//   k_corr_cols : columns b of W  ->  N1-point inverse FFT  ->  e^{+i pi m/N}/M  ->  |Re|, |Im|  ->  max / write
+//
+// Both kernels keep one radix-8 (radix-10) butterfly per thread in registers, in packed complex
+// arithmetic (cpx2.cuh: FADD2/FMUL2/FFMA2), read the first pass straight from global memory and hand
+// the last pass straight to the epilogue.  All twiddles and all shared-memory addresses are loop
+// invariants of the per-CTA loop over units: the XOR-swizzled exchange layouts (fft_fast.cuh) reduce to
+// "thread constant + immediate" for loads and "thread constant ^ immediate" for stores.
+#include "fft_fast.cuh"
+#include "internal.h"
+
+namespace apd {
+
+struct __align__(16) UnitDesc {
+    const float2* xs;     // section spectrum of the unit's (chunk, group), row 0
+    const float2* hs;     // spectrum of the unit's reversed clip, row 0
+    int n_out;            // length of the 'full' correlation; < 0: slot not in use
+    int max_idx;          // index into unit_max_bits
+    float mc;             // write mode: max(self max, unit max)  (apd.py:493)
+    int pad;
+};
+static_assert(sizeof(UnitDesc) == 32, "UnitDesc is loaded as two 16-byte words");
+
+__global__ void k_unit_desc(UnitSrc U, UnitCtx C, const float2* __restrict__ spec, long long spec_stride,
+                            InvOut O, int nunits, int write, UnitDesc* __restrict__ D)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nunits) return;
+    UnitDesc d;
+    int2 unit;
+    if (!get_unit(U, u, &unit)) {
+        d.xs = nullptr; d.hs = nullptr; d.n_out = -1; d.max_idx = 0; d.mc = 1.0f; d.pad = 0;
+        D[u] = d;
+        return;
+    }
+    long long start;
+    int n;
+    section_bounds(C.geoms[C.clip_group[unit.y]], unit.x, start, n);
+    d.xs = spec + (long long)unit.x * spec_stride + C.clip_spec_off[unit.y];
+    d.hs = C.clip_spec[unit.y];
+    d.n_out = n > 0 ? n + C.clip_len[unit.y] - 1 : 0;
+    d.max_idx = unit.x * O.n_clips + unit.y;
+    d.mc = 1.0f;
+    if (write) d.mc = fmaxf(O.self_max[unit.y], __uint_as_float(O.unit_max_bits[d.max_idx]));
+    d.pad = 0;
+    D[u] = d;
+}
+
+// ---------------------------------------------------------------- shared-memory access by 32-bit address
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF> __device__ __forceinline__ c2 lds(unsigned a)
+{
+    c2 r;
+    asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(r.v) : "r"(a), "n"(OFF) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts(unsigned a, c2 v)
+{
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v.v) : "memory");
+}
+__device__ __forceinline__ c2 ldg_nc(const c2* p)          // read-only path, keeps the line in L1
+{
+    c2 r;
+    r.v = __ldg(reinterpret_cast<const unsigned long long*>(p));
+    return r;
+}
+__device__ __forceinline__ c2 ldg_stream(const c2* p)      // streamed once: do not pollute L1
+{
+    c2 r;
+    asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(r.v) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ UnitDesc load_desc(const UnitDesc* p)
+{
+    UnitDesc d;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    d.xs = reinterpret_cast<const float2*>(((unsigned long long)a.y << 32) | a.x);
+    d.hs = reinterpret_cast<const float2*>(((unsigned long long)a.w << 32) | a.z);
+    d.n_out = (int)b.x; d.max_idx = (int)b.y; d.mc = __uint_as_float(b.z); d.pad = 0;
+    return d;
+}
+
+constexpr int kN2 = 512;          // row length (complex)
+constexpr int kRowsPerCta = 4;    // 64 threads per row
+
+// ---------------------------------------------------------------- rows
+// 64 threads (two warps) per row, kRowsPerCta rows per CTA; the two warps of a row synchronise among
+// themselves only (named barrier q + 1).  Exchange layout of a row: slot(e) = e ^ ((e >> 3) & 15).
+//   loads  e = j + 64 r            : 8 * (j ^ (j >> 3)) [^ 64 for odd r] + 512 r      (constant + immediate)
+//   stores e = 8 j + r      (pass 1): 8 * ((8 j) ^ (j & 15))            ^ (8 r)       (constant ^ immediate)
+//   stores e = 64 (j >> 3) + (j & 7) + 8 r (pass 2):
+//                                     8 * (64 (j >> 3) + 8 ((j >> 3) & 1) + (j & 7)) ^ (72 r)
+template <int R>
+struct RowAddr {
+    unsigned ld0, ld1, st1, st2;
+    __device__ __forceinline__ RowAddr(unsigned row_base, int j)
+    {
+        ld0 = row_base + 8u * (unsigned)(j ^ (j >> 3));
+        ld1 = ld0 ^ 64u;
+        st1 = row_base + 8u * (unsigned)((8 * j) ^ (j & 15));
+        st2 = row_base + 8u * (unsigned)(64 * (j >> 3) + 8 * ((j >> 3) & 1) + (j & 7));
+    }
+};
+
+template <int R> __device__ __forceinline__ c2 row_ld(const RowAddr<8>& A)
+{
+    return (R & 1) ? lds<512 * R>(A.ld1) : lds<512 * R>(A.ld0);
+}
+
+#define APD_ROW_LOAD8(A, v)                                                                       \
+    v[0] = row_ld<0>(A); v[1] = row_ld<1>(A); v[2] = row_ld<2>(A); v[3] = row_ld<3>(A);          \
+    v[4] = row_ld<4>(A); v[5] = row_ld<5>(A); v[6] = row_ld<6>(A); v[7] = row_ld<7>(A);
+
+template <bool KEEP_H>
+__global__ void __launch_bounds__(kRowsPerCta * 64, KEEP_H ? 2 : 3)
+k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+{
+    __shared__ __align__(1024) c2 buf[kRowsPerCta * kN2];
+    const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int c = bx * kRowsPerCta + q;
+    const RowAddr<8> A(smem_addr(buf + q * kN2), j);
+    float2 tw2[8], tw3[8], fs[8];
+    pass_twiddles<8, +1, 8>(j, tw2);
+    pass_twiddles<8, +1, 64>(j, tw3);
+    {   // outputs b = j + 64 r ; four-step twiddle w_M^{+b c} = base * step^r
+        const float invM = 1.0f / (float)M;
+        geometric<8>(twiddle_frac(j * c, invM, +1.0f), twiddle_frac(64 * c, invM, +1.0f), fs);
+    }
+    const long long row_off = (long long)c * kN2 + j;
+    const int u_end = min(nunits, (by + 1) * per);
+    const float2* cur_hs = nullptr;
+    c2 h[8];
+    for (int u = by * per; u < u_end; ++u) {
+        const UnitDesc d = load_desc(D + u);
+        if (d.n_out < 0) continue;
+        const c2* __restrict__ xs = reinterpret_cast<const c2*>(d.xs + row_off);
+        const c2* __restrict__ hs = reinterpret_cast<const c2*>(d.hs + row_off);
+        c2 v[8];
+        if (KEEP_H) {
+            // consecutive units of a launch share the clip (clip-major order): its row stays in registers
+            if (d.hs != cur_hs) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) h[r] = ldg_nc(hs + 64 * r);
+                cur_hs = d.hs;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = cmul(ldg_stream(xs + 64 * r), h[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = cmul(ldg_stream(xs + 64 * r), ldg_nc(hs + 64 * r));
+        }
+        Dft2<8, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts(A.st1 ^ (8u * r), v[r]);
+        group_sync<64>(q + 1);
+        APD_ROW_LOAD8(A, v)
+        group_sync<64>(q + 1);
+        bfly_tw<8>(v, tw2);
+        Dft2<8, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts(A.st2 ^ (72u * r), v[r]);
+        group_sync<64>(q + 1);
+        APD_ROW_LOAD8(A, v)
+        group_sync<64>(q + 1);
+        bfly_tw<8>(v, tw3);
+        Dft2<8, +1>::run(v);
+        c2* __restrict__ out = reinterpret_cast<c2*>(W + (long long)u * M + row_off);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) out[64 * r] = cmul(v[r], fs[r]);
+    }
+}
+
+// ---------------------------------------------------------------- columns
+// TB = 4 adjacent columns on the lanes (q = tid % 4), butterfly j = tid / 4; N1 = R0 R1 R2 = 8*8*8 or
+// 8*8*10.  Exchange layout: word(e, q) = 4 * (e ^ ((e >> 3) & 3)) + q.
+//   loads  e = j + T r  (T = N1/8 in pass 2, 64 in pass 3): 32 (j ^ s) + 8 q + 32 T r, s = (j >> 3) & 3,
+//          and for T = 80 odd r use s ^ 2                                    (constant + immediate)
+//   stores e = 8 j + r (pass 1)                    : (32 (8 j + (j & 3)) + 8 q) ^ (32 r)
+//   stores e = 64 (j >> 3) + (j & 7) + 8 r (pass 2): (32 (64 (j >> 3) + (j & 7)) + 8 q) ^ (32 (8 r + (r & 3)))
+constexpr int kTB = 4;
+
+// e^{i pi r / (2 R)}, r < R: the r-dependent part of the post-twiddle (immediates after unrolling)
+__device__ __forceinline__ float2 post_const8(int r)
+{
+    constexpr float c[8] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f};
+    constexpr float s[8] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f, 0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
+    return make_float2(c[r], s[r]);
+}
+__device__ __forceinline__ float2 post_const10(int r)
+{
+    constexpr float c[10] = {1.0f, 0.98768834059513777f, 0.95105651629515353f, 0.8910065241883679f, 0.80901699437494745f, 0.70710678118654757f, 0.58778525229247314f, 0.4539904997395468f, 0.30901699437494745f, 0.15643446504023092f};
+    constexpr float s[10] = {0.0f, 0.15643446504023087f, 0.3090169943749474f, 0.45399049973954675f, 0.58778525229247314f, 0.70710678118654746f, 0.80901699437494745f, 0.89100652418836779f, 0.95105651629515353f, 0.98768834059513777f};
+    return make_float2(c[r], s[r]);
+}
+
+template <int OFF> __device__ __forceinline__ c2 lds_sel(unsigned a0, unsigned a1, bool odd)
+{
+    return odd ? lds<OFF>(a1) : lds<OFF>(a0);
+}
+
+template <class S, bool WRITE>
+__global__ void __launch_bounds__(kTB * (S::N / 8), S::N == 512 ? 3 : 2)
+k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
+            unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride, int swap)
+{
+    constexpr int N1 = S::N;
+    constexpr int T1 = N1 / 8;            // butterflies per column in the radix-8 passes
+    constexpr int R2 = S::R2;             // last radix: 8 or 10
+    constexpr int NLAST = N1 / R2;        // 64 butterflies in the last pass
+    constexpr int NW = kTB * T1 / 32;     // warps per CTA
+    // the store addresses are formed as (constant ^ immediate) with immediates up to 2^11: the buffer base
+    // must be 2 KB aligned, which is more than a static __shared__ declaration guarantees
+    __shared__ __align__(1024) c2 raw[N1 * kTB + 128];
+    __shared__ float red[NW];
+    const int q = threadIdx.x % kTB, j = threadIdx.x / kTB;
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int bcol = bx * kTB + q;
+    const unsigned sb = ((smem_addr(raw) + 2047u) & ~2047u) + 8u * (unsigned)q;
+    const unsigned ld_a = sb + 32u * (unsigned)(j ^ ((j >> 3) & 3));                 // even r (and all r if T = 64)
+    const unsigned ld_b = sb + 32u * (unsigned)(j ^ (((j >> 3) & 3) ^ 2));           // odd r when T = 80
+    const unsigned st1 = sb + 32u * (unsigned)(8 * j + (j & 3));
+    const unsigned st2 = sb + 32u * (unsigned)(64 * (j >> 3) + (j & 7));
+    float2 tw2[8], tw3[R2];
+    pass_twiddles<8, +1, 8>(j, tw2);
+    pass_twiddles<R2, +1, 64>(j, tw3);
+    {
+        // post-twiddle e^{+i pi m / N} / M with m = (j + 64 r) 512 + b = base * e^{i pi r / (2 R2)}: the base
+        // is a per-thread scalar that commutes with the last butterfly, so it is folded into that pass's
+        // input twiddles (r = 0 included); the r-dependent part is a compile-time constant (below).
+        const float invN = 1.0f / (2.0f * (float)M);
+        const float invM = 1.0f / (float)M;
+        const float2 base = cispif((float)((j % NLAST) * kN2 + bcol) * invN);
+        const float2 sbase = make_float2(base.x * invM, base.y * invM);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) tw3[r] = cmul(tw3[r], sbase);
+    }
+    const long long col_off = (long long)j * kN2 + bcol;
+    const int m0 = (j % NLAST) * kN2 + bcol;                 // output index of r = 0; r adds 64 * 512
+    const int u_end = min(nunits, (by + 1) * per);
+    for (int u = by * per; u < u_end; ++u) {
+        const UnitDesc d = load_desc(D + u);
+        if (d.n_out < 0) continue;
+        const c2* __restrict__ in = reinterpret_cast<const c2*>(W + (long long)u * M + col_off);
+        c2 v[R2 > 8 ? R2 : 8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = ldg_stream(in + (long long)T1 * kN2 * r);
+        Dft2<8, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts(st1 ^ (32u * r), v[r]);
+        __syncthreads();
+        if (N1 == 512) {
+            v[0] = lds<0>(ld_a); v[1] = lds<32 * 64 * 1>(ld_a); v[2] = lds<32 * 64 * 2>(ld_a); v[3] = lds<32 * 64 * 3>(ld_a);
+            v[4] = lds<32 * 64 * 4>(ld_a); v[5] = lds<32 * 64 * 5>(ld_a); v[6] = lds<32 * 64 * 6>(ld_a); v[7] = lds<32 * 64 * 7>(ld_a);
+        } else {
+            v[0] = lds<0>(ld_a); v[1] = lds<32 * 80 * 1>(ld_b); v[2] = lds<32 * 80 * 2>(ld_a); v[3] = lds<32 * 80 * 3>(ld_b);
+            v[4] = lds<32 * 80 * 4>(ld_a); v[5] = lds<32 * 80 * 5>(ld_b); v[6] = lds<32 * 80 * 6>(ld_a); v[7] = lds<32 * 80 * 7>(ld_b);
+        }
+        __syncthreads();
+        bfly_tw<8>(v, tw2);
+        Dft2<8, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts(st2 ^ (32u * (8 * r + (r & 3))), v[r]);
+        __syncthreads();
+        float best = 0.0f;
+        if (N1 == 512 || j < NLAST) {
+            v[0] = lds<0>(ld_a); v[1] = lds<32 * 64 * 1>(ld_a); v[2] = lds<32 * 64 * 2>(ld_a); v[3] = lds<32 * 64 * 3>(ld_a);
+            v[4] = lds<32 * 64 * 4>(ld_a); v[5] = lds<32 * 64 * 5>(ld_a); v[6] = lds<32 * 64 * 6>(ld_a); v[7] = lds<32 * 64 * 7>(ld_a);
+            if (R2 == 10) { v[8] = lds<32 * 64 * 8>(ld_a); v[9] = lds<32 * 64 * 9>(ld_a); }
+#pragma unroll
+            for (int r = 0; r < R2; ++r) v[r] = cmul(v[r], tw3[r]);
+            Dft2<R2, +1>::run(v);
+            float* __restrict__ out = WRITE ? corr + (long long)u * corr_stride : nullptr;
+            const int lim0 = d.n_out - m0, lim1 = d.n_out - M - m0;      // valid iff 32768 r < lim
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                // e^{i pi r / (2 R2)} as immediates
+                const float2 pc = R2 == 8 ? post_const8(r < 8 ? r : 0) : post_const10(r);
+                const float cr = pc.x, sr = pc.y;
+                float zr, zi;
+                split(r == 0 ? v[0] : cmul(v[r], cr, sr), zr, zi);
+                const float y0 = fabsf(zr), y1 = fabsf(zi);
+                if (WRITE) {
+                    if (64 * kN2 * r < lim0) out[m0 + 64 * kN2 * r] = y0 / d.mc;          // apd.py:494 (float32 divide)
+                    if (64 * kN2 * r < lim1) out[m0 + 64 * kN2 * r + M] = y1 / d.mc;
+                } else {
+                    if (64 * kN2 * r < lim0) best = fmaxf(best, y0);
+                    if (64 * kN2 * r < lim1) best = fmaxf(best, y1);
+                }
+            }
+        }
+        if (!WRITE) {
+            best = warp_max(best);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        }
+        __syncthreads();                  // exchange buffer free for the next unit; red[] complete
+        if (!WRITE && threadIdx.x < 32) {
+            float t = threadIdx.x < NW ? red[threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + d.max_idx, __float_as_uint(t));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launcher
+static int env_int2(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+bool corr_inv_supported(const Fft4Plan& P) { return P.N2 == kN2 && (P.N1 == 512 || P.N1 == 640); }
+
+size_t corr_inv_desc_bytes(int nunits) { return sizeof(UnitDesc) * (size_t)(nunits > 0 ? nunits : 1); }
+
+void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
+                     int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st)
+{
+    static const int per_max = std::max(1, env_int2("APD_B200_PER", 8));
+    static const int keep_h = env_int2("APD_B200_KEEP_H", 1);
+    static const int swap = env_int2("APD_B200_SWAP", 1);
+    UnitDesc* D = static_cast<UnitDesc*>(desc);
+    k_unit_desc<<<(nunits + 127) / 128, 128, 0, st>>>(U, C, spec, spec_slab, out, nunits, write ? 1 : 0, D);
+    // keep at least ~8 CTAs per SM in the grid; otherwise amortise the twiddles over up to `per` units
+    int per = per_max;
+    while (per > 1 && (long long)((nunits + per - 1) / per) * 64 < 148 * 8) per >>= 1;
+    const int ny = (nunits + per - 1) / per;
+    const int row_tiles = P.N1 / kRowsPerCta, col_tiles = kN2 / kTB;
+    const dim3 gr = swap ? dim3(ny, row_tiles) : dim3(row_tiles, ny);
+    const dim3 gc = swap ? dim3(ny, col_tiles) : dim3(col_tiles, ny);
+    if (keep_h) k_corr_rows<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
+    else k_corr_rows<false><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
+    if (P.N1 == 512) {
+        if (write) k_corr_cols<Shape512, true><<<gc, kTB * 64, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, out.corr, out.corr_stride, swap);
+        else k_corr_cols<Shape512, false><<<gc, kTB * 64, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, out.corr, out.corr_stride, swap);
+    } else {
+        if (write) k_corr_cols<Shape640, true><<<gc, kTB * 80, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, out.corr, out.corr_stride, swap);
+        else k_corr_cols<Shape640, false><<<gc, kTB * 80, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, out.corr, out.corr_stride, swap);
+    }
+}
+
+}  // namespace apd

@@ -191,91 +191,56 @@ k_inv_cols(Fft4Plan P, UnitCtx C, UnitSrc U, const float2* __restrict__ W, InvOu
 }
 
 // ------------------------------------------------------------------ fast kernels (hot shapes)
+// Forward transforms of the hot shapes (the inverse ones live in corr_inv.cu).
 // Row kernels handle N2 = 512 = 8*8*8 with 64 threads per row (one radix-8 butterfly per thread per
 // pass); column kernels handle N1 in {512 = 8*8*8, 640 = 8*8*10} with one thread per butterfly and
-// TB adjacent columns on the lanes.  See fft_fast.cuh.
+// TB adjacent columns on the lanes.  All complex arithmetic is packed (cpx2.cuh, fft_fast.cuh).
 constexpr int kRowN = 512;
 constexpr int kRowPitch = kRowN;
 __device__ __forceinline__ int rpad(int e) { return e ^ ((e >> 3) & 15); }
 template <int TB> __device__ __forceinline__ int cswz(int e) { return TB == 8 ? (e ^ ((e >> 3) & 1)) : (e ^ ((e >> 3) & 3)); }
+__device__ __forceinline__ c2 ldg_c2(const c2* p)
+{
+    c2 r;
+    r.v = __ldg(reinterpret_cast<const unsigned long long*>(p));
+    return r;
+}
 
 // Every fast kernel fixes its tile (rows c0.. / columns b0..) and loops over `per` consecutive
 // transforms of the batch (units or sections), so all twiddles are loop invariants in registers.
-template <int TR>
-__global__ void __launch_bounds__(TR * 64)
-k_inv_rows_fast(Fft4Plan P, const float2* __restrict__ spec, long long spec_stride, UnitSrc U, UnitCtx C,
-                float2* __restrict__ W, int nunits, int per)
-{
-    __shared__ float2 buf[TR * kRowPitch];
-    const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
-    const int c = blockIdx.x * TR + q;
-    float2* b = buf + q * kRowPitch;
-    float2 tw2[8], tw3[8], fs[8];
-    pass_twiddles<8, +1, 8>(j, tw2);
-    pass_twiddles<8, +1, 64>(j, tw3);
-    {   // outputs b_idx = j + 64 r ; four-step twiddle w_M^{+b c} = base * step^r
-        const float invM = 1.0f / (float)P.M;
-        geometric<8>(twiddle_frac(j * c, invM, +1.0f), twiddle_frac(64 * c, invM, +1.0f), fs);
-    }
-    const int u_end = min(nunits, (int)(blockIdx.y + 1) * per);
-    for (int u = blockIdx.y * per; u < u_end; ++u) {
-        int2 unit;
-        if (!get_unit(U, u, &unit)) continue;
-        const float2* __restrict__ xs = spec + (long long)unit.x * spec_stride + C.clip_spec_off[unit.y] +
-                                        (long long)c * kRowN;
-        const float2* __restrict__ hs = C.clip_spec[unit.y] + (long long)c * kRowN;
-        float2 v[8];
-        bfly_ld<8, kRowN>(j, [&](int e) { return cmul(xs[e], __ldg(&hs[e])); }, v);
-        Dft<8, +1>::run(v);
-        bfly_store<8, 1>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
-        __syncthreads();
-        bfly_ld<8, kRowN>(j, [&](int e) { return b[rpad(e)]; }, v);
-        __syncthreads();
-        bfly_tw<8>(v, tw2);
-        Dft<8, +1>::run(v);
-        bfly_store<8, 8>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
-        __syncthreads();
-        bfly_ld<8, kRowN>(j, [&](int e) { return b[rpad(e)]; }, v);
-        __syncthreads();
-        bfly_tw<8>(v, tw3);
-        Dft<8, +1>::run(v);
-        float2* __restrict__ out = W + (long long)u * P.M + (long long)c * kRowN;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) out[j + 64 * r] = cmul(v[r], fs[r]);
-    }
-}
-
+// In the row kernels the 64 threads (two warps) of a row synchronise among themselves only
+// (named barrier q + 1), so the rows of a CTA drift apart and overlap each other's memory waits.
 template <int TR>
 __global__ void __launch_bounds__(TR * 64)
 k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ spec, long long spec_stride,
                 int nsec, int per)
 {
-    __shared__ float2 buf[TR * kRowPitch];
+    __shared__ c2 buf[TR * kRowPitch];
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
     const int c = blockIdx.x * TR + q;
-    float2* b = buf + q * kRowPitch;
+    c2* b = buf + q * kRowPitch;
     float2 tw2[8], tw3[8];
     pass_twiddles<8, -1, 8>(j, tw2);
     pass_twiddles<8, -1, 64>(j, tw3);
     const int s_end = min(nsec, (int)(blockIdx.y + 1) * per);
     for (int sec = blockIdx.y * per; sec < s_end; ++sec) {
-        const float2* __restrict__ in = T + (long long)sec * P.M + (long long)c * kRowN;
-        float2 v[8];
+        const c2* __restrict__ in = reinterpret_cast<const c2*>(T + (long long)sec * P.M + (long long)c * kRowN);
+        c2 v[8];
         bfly_ld<8, kRowN>(j, [&](int e) { return in[e]; }, v);
-        Dft<8, -1>::run(v);
-        bfly_store<8, 1>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
-        __syncthreads();
+        Dft2<8, -1>::run(v);
+        bfly_store<8, 1>(j, [&](int e, c2 x) { b[rpad(e)] = x; }, v);
+        group_sync<64>(q + 1);
         bfly_ld<8, kRowN>(j, [&](int e) { return b[rpad(e)]; }, v);
-        __syncthreads();
+        group_sync<64>(q + 1);
         bfly_tw<8>(v, tw2);
-        Dft<8, -1>::run(v);
-        bfly_store<8, 8>(j, [&](int e, float2 x) { b[rpad(e)] = x; }, v);
-        __syncthreads();
+        Dft2<8, -1>::run(v);
+        bfly_store<8, 8>(j, [&](int e, c2 x) { b[rpad(e)] = x; }, v);
+        group_sync<64>(q + 1);
         bfly_ld<8, kRowN>(j, [&](int e) { return b[rpad(e)]; }, v);
-        __syncthreads();
+        group_sync<64>(q + 1);
         bfly_tw<8>(v, tw3);
-        Dft<8, -1>::run(v);
-        float2* __restrict__ out = spec + (long long)sec * spec_stride + (long long)c * kRowN;
+        Dft2<8, -1>::run(v);
+        c2* __restrict__ out = reinterpret_cast<c2*>(spec + (long long)sec * spec_stride + (long long)c * kRowN);
 #pragma unroll
         for (int r = 0; r < 8; ++r) out[j + 64 * r] = v[r];
     }
@@ -289,7 +254,7 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, const double* __restrict__ gains, int
 {
     constexpr int N1 = S::N;
     constexpr int NLAST = N1 / S::R2;
-    __shared__ float2 buf[N1 * TB];
+    __shared__ c2 buf[N1 * TB];
     const int q = threadIdx.x % TB, j = threadIdx.x / TB;
     const int bcol = blockIdx.x * TB + q;
     const int M = P.M, N2 = P.N2;
@@ -311,114 +276,32 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, const double* __restrict__ gains, int
         section_bounds(G, sec, start, n);
         const float* __restrict__ x = G.audio + (start - G.base);
         const double gain = gains ? gains[(long long)sec * gain_stride] : 1.0;
-        float2 v[10];
+        c2 v[10];
         bfly_ld<S::R0, N1>(j, [&](int e) {
             const int m = e * N2 + bcol;
             const float x0 = m < n ? normalize_sample(x[m], gain) : 0.0f;
             const float x1 = m + M < n ? normalize_sample(x[m + M], gain) : 0.0f;
-            return make_float2(x0, -x1);
+            return mk(x0, -x1);
         }, v);
 #pragma unroll
         for (int r = 0; r < S::R0; ++r) v[r] = cmul(v[r], pre[r]);
-        Dft<S::R0, -1>::run(v);
-        bfly_store<S::R0, 1>(j, [&](int e, float2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
+        Dft2<S::R0, -1>::run(v);
+        bfly_store<S::R0, 1>(j, [&](int e, c2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
         __syncthreads();
         bfly_ld<S::R1, N1>(j, [&](int e) { return buf[cswz<TB>(e) * TB + q]; }, v);
         __syncthreads();
         bfly_tw<S::R1>(v, tw2);
-        Dft<S::R1, -1>::run(v);
-        bfly_store<S::R1, S::R0>(j, [&](int e, float2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
+        Dft2<S::R1, -1>::run(v);
+        bfly_store<S::R1, S::R0>(j, [&](int e, c2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
         __syncthreads();
         if (j < NLAST) {
             bfly_ld<S::R2, N1>(j, [&](int e) { return buf[cswz<TB>(e) * TB + q]; }, v);
             bfly_tw<S::R2>(v, tw3);
-            Dft<S::R2, -1>::run(v);
-            float2* __restrict__ out = T + (long long)sec * M;
+            Dft2<S::R2, -1>::run(v);
+            c2* __restrict__ out = reinterpret_cast<c2*>(T + (long long)sec * M);
 #pragma unroll
             for (int r = 0; r < S::R2; ++r)
                 out[(long long)(j + r * NLAST) * N2 + bcol] = cmul(v[r], fs[r]);
-        }
-        __syncthreads();
-    }
-}
-
-template <class S, int TB, bool WRITE>
-__global__ void __launch_bounds__(TB * (S::N / 8))
-k_inv_cols_fast(Fft4Plan P, UnitCtx C, UnitSrc U, const float2* __restrict__ W, InvOut O, int nunits, int per)
-{
-    constexpr int N1 = S::N;
-    constexpr int NLAST = N1 / S::R2;
-    __shared__ float2 buf[N1 * TB];
-    __shared__ float red[32];
-    const int q = threadIdx.x % TB, j = threadIdx.x / TB;
-    const int bcol = blockIdx.x * TB + q;
-    const int M = P.M, N2 = P.N2;
-    float2 tw2[S::R1], tw3[S::R2], post[S::R2];
-    pass_twiddles<S::R1, +1, S::R0>(j, tw2);
-    pass_twiddles<S::R2, +1, S::R0 * S::R1>(j, tw3);
-    {
-        // post-twiddle e^{+i pi m / N} / M, m = (j + r NLAST) N2 + b = base * (e^{i pi / (2 R2)})^r
-        const float invN = 1.0f / (2.0f * (float)M);
-        const float invM = 1.0f / (float)M;
-        const float2 base = cispif((float)((j % NLAST) * N2 + bcol) * invN);
-        geometric<S::R2>(make_float2(base.x * invM, base.y * invM), cispif(0.5f / (float)S::R2), post);
-    }
-    const int u_end = min(nunits, (int)(blockIdx.y + 1) * per);
-    for (int u = blockIdx.y * per; u < u_end; ++u) {
-        int2 unit;
-        if (!get_unit(U, u, &unit)) continue;
-        const float2* __restrict__ in = W + (long long)u * M;
-        float2 v[10];
-        bfly_ld<S::R0, N1>(j, [&](int e) { return in[(long long)e * N2 + bcol]; }, v);
-        Dft<S::R0, +1>::run(v);
-        bfly_store<S::R0, 1>(j, [&](int e, float2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
-        __syncthreads();
-        bfly_ld<S::R1, N1>(j, [&](int e) { return buf[cswz<TB>(e) * TB + q]; }, v);
-        __syncthreads();
-        bfly_tw<S::R1>(v, tw2);
-        Dft<S::R1, +1>::run(v);
-        bfly_store<S::R1, S::R0>(j, [&](int e, float2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
-        __syncthreads();
-        float best = 0.0f;
-        if (j < NLAST) {
-            bfly_ld<S::R2, N1>(j, [&](int e) { return buf[cswz<TB>(e) * TB + q]; }, v);
-            bfly_tw<S::R2>(v, tw3);
-            Dft<S::R2, +1>::run(v);
-            long long start;
-            int n;
-            section_bounds(C.geoms[C.clip_group[unit.y]], unit.x, start, n);
-            const int n_out = n > 0 ? n + C.clip_len[unit.y] - 1 : 0;
-            float mc = 1.0f;
-            float* __restrict__ corr = nullptr;
-            if (WRITE) {
-                const float um = __uint_as_float(O.unit_max_bits[(long long)unit.x * O.n_clips + unit.y]);
-                mc = fmaxf(O.self_max[unit.y], um);                       // apd.py:493
-                corr = O.corr + (long long)u * O.corr_stride;
-            }
-#pragma unroll
-            for (int r = 0; r < S::R2; ++r) {
-                const int m = (j + r * NLAST) * N2 + bcol;
-                const float2 z = cmul(v[r], post[r]);
-                const float y0 = fabsf(z.x), y1 = fabsf(z.y);
-                if (WRITE) {
-                    if (m < n_out) corr[m] = y0 / mc;                      // apd.py:494 (float32 divide)
-                    if (m + M < n_out) corr[m + M] = y1 / mc;
-                } else {
-                    if (m < n_out) best = fmaxf(best, y0);
-                    if (m + M < n_out) best = fmaxf(best, y1);
-                }
-            }
-        }
-        if (!WRITE) {
-            best = warp_max(best);
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
-                t = warp_max(t);
-                if (threadIdx.x == 0)
-                    atomicMax(&O.unit_max_bits[(long long)unit.x * O.n_clips + unit.y], __float_as_uint(t));
-            }
         }
         __syncthreads();
     }
@@ -452,20 +335,6 @@ static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G
         k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, 0, st>>>(P, G, gains, gain_stride, scratch, nsec, per);
     else
         k_fwd_cols_fast<Shape640, TB><<<gc, TB * 80, 0, st>>>(P, G, gains, gain_stride, scratch, nsec, per);
-}
-
-template <int TB>
-static void launch_inv_cols_fast(int fs, const Fft4Plan& P, const UnitCtx& C, const UnitSrc& U, float2* scratch,
-                                 const InvOut& out, bool write, int nunits, int per, int ny, cudaStream_t st)
-{
-    dim3 gc(P.N2 / TB, ny);
-    if (fs == 512) {
-        if (write) k_inv_cols_fast<Shape512, TB, true><<<gc, TB * 64, 0, st>>>(P, C, U, scratch, out, nunits, per);
-        else k_inv_cols_fast<Shape512, TB, false><<<gc, TB * 64, 0, st>>>(P, C, U, scratch, out, nunits, per);
-    } else {
-        if (write) k_inv_cols_fast<Shape640, TB, true><<<gc, TB * 80, 0, st>>>(P, C, U, scratch, out, nunits, per);
-        else k_inv_cols_fast<Shape640, TB, false><<<gc, TB * 80, 0, st>>>(P, C, U, scratch, out, nunits, per);
-    }
 }
 
 static int fast_shape(const Fft4Plan& P)
@@ -605,17 +474,13 @@ void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains
 }
 
 void launch_inverse(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab,
-                    const UnitSrc& U, int nunits, float2* scratch, const InvOut& out, bool write, cudaStream_t st)
+                    const UnitSrc& U, int nunits, float2* scratch, void* desc, const InvOut& out, bool write,
+                    cudaStream_t st)
 {
     if (nunits <= 0) return;
     ensure_attrs();
-    const int fs = fast_shape(P);
-    if (fs) {
-        const int per = fast_per(nunits), ny = (nunits + per - 1) / per;
-        dim3 gr(P.N1 / kFastTR, ny);
-        k_inv_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, spec, spec_slab, U, C, scratch, nunits, per);
-        if (fast_tb() == 8) launch_inv_cols_fast<8>(fs, P, C, U, scratch, out, write, nunits, per, ny, st);
-        else launch_inv_cols_fast<4>(fs, P, C, U, scratch, out, write, nunits, per, ny, st);
+    if (corr_inv_supported(P) && desc) {
+        launch_corr_inv(P, C, spec, spec_slab, U, nunits, scratch, desc, out, write, st);
         return;
     }
     dim3 gr(P.N1 >> P.tr_log2, nunits), gc(P.N2 >> P.tb_log2, nunits);

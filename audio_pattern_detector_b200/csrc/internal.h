@@ -47,9 +47,10 @@ __host__ __device__ inline void section_bounds(const SectionGeom& g, int ci, lon
 struct UnitSrc {
     const int2* list;        // explicit (ci, clip) pairs (phase 2), or nullptr for the dense layout below
     const int* list_begin;   // phase 2: this launch owns list positions [list_begin[0], list_begin[1])
-    const int* shape_clips;  // dense: clip = shape_clips[u % ns], ci = u / ns
-    int ns;
+    const int* shape_clips;  // dense: clip-major, clip = shape_clips[u / nb], ci = u % nb (consecutive units share
+    int ns;                  //        a clip, so its spectrum rows stay in L1/L2 across the per-CTA unit loop)
     int u0;                  // first unit of this launch (offset into list / dense numbering)
+    int nb;                  // dense: chunks in the batch
 };
 
 // Returns false if launch-local unit u is not this launch's to process.
@@ -61,7 +62,7 @@ __device__ __forceinline__ bool get_unit(const UnitSrc& s, int u, int2* unit)
         *unit = s.list[u];
         return true;
     }
-    *unit = make_int2(u / s.ns, s.shape_clips[u % s.ns]);
+    *unit = s.nb > 0 ? make_int2(u % s.nb, s.shape_clips[u / s.nb]) : make_int2(u / s.ns, s.shape_clips[u % s.ns]);
     return true;
 }
 
@@ -92,7 +93,16 @@ void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains
                     float2* scratch /* nsec*M */, float2* spec, long long spec_stride, cudaStream_t st);
 // Fused spectral multiply + inverse FFT + |.| ; write == false: per-unit max, write == true: normalised
 // correlation into O.corr.  scratch holds nunits * M complex (launch-local unit index).
+// desc: device scratch of corr_inv_desc_bytes(nunits) bytes (per-unit descriptors of the hot-shape kernels).
 void launch_inverse(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab,
-                    const UnitSrc& U, int nunits, float2* scratch, const InvOut& out, bool write, cudaStream_t st);
+                    const UnitSrc& U, int nunits, float2* scratch, void* desc, const InvOut& out, bool write,
+                    cudaStream_t st);
+// returns the number of kernels launched
+
+// corr_inv.cu: the register-resident packed-arithmetic kernels for M = N1 x 512, N1 in {512, 640}
+bool corr_inv_supported(const Fft4Plan& P);
+size_t corr_inv_desc_bytes(int nunits);
+void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
+                     int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st);
 
 }  // namespace apd
