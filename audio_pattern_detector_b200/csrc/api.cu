@@ -62,6 +62,10 @@ struct ShapeClass {
     Fft4Plan plan;
     std::vector<int> clips;
     int* d_clips = nullptr;
+    std::vector<int> groups;              // sliding-window groups of this shape
+    int* d_group_halo = nullptr;
+    int* d_group_index = nullptr;
+    long long* d_group_spec_off = nullptr;
 };
 
 template <typename T>
@@ -306,8 +310,8 @@ static int self_correlation(apd_ctx* c, ClipHost& cl, InitTmp& t)
     CK(dalloc(&sb, (size_t)P.M));
     CK(dalloc(&scr, (size_t)P.M));
     SectionGeom Ga{cl.d_norm, 0, L, L, 0, 0}, Gb{cl.d_rev, 0, L, L, 0, 0};
-    launch_forward(P, Ga, nullptr, 0, 1, scr, sa, P.M, 0);
-    launch_forward(P, Gb, nullptr, 0, 1, scr, sb, P.M, 0);
+    launch_forward(P, Ga, FwdGroups{nullptr, nullptr, nullptr, 0}, nullptr, 0, 1, scr, sa, P.M, 0);
+    launch_forward(P, Gb, FwdGroups{nullptr, nullptr, nullptr, 0}, nullptr, 0, 1, scr, sb, P.M, 0);
     CK(cudaMemset(t.max_bits, 0, sizeof(unsigned int)));
     CK(cudaMemcpy(t.ints + 1, &L, sizeof(int), cudaMemcpyHostToDevice));
     const float2* hp = sb;
@@ -397,14 +401,26 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
             free_plan(&plan);
         }
         g.shape = shape;
+        c->shapes[shape].groups.push_back((int)(&g - &c->groups[0]));
         for (int p : g.clips) c->shapes[shape].clips.push_back(p);
         g.spec_off = c->spec_slab;
         c->spec_slab += c->shapes[shape].plan.M;
         max_M = std::max<long long>(max_M, c->shapes[shape].plan.M);
     }
+    size_t max_class_groups = 1;
     for (auto& sc : c->shapes) {
         std::sort(sc.clips.begin(), sc.clips.end());
         CK(upload(&sc.d_clips, sc.clips));
+        std::vector<int> halo;
+        std::vector<long long> off;
+        for (int g : sc.groups) {
+            halo.push_back(c->groups[g].halo);
+            off.push_back(c->groups[g].spec_off);
+        }
+        CK(upload(&sc.d_group_halo, halo));
+        CK(upload(&sc.d_group_index, sc.groups));
+        CK(upload(&sc.d_group_spec_off, off));
+        max_class_groups = std::max(max_class_groups, sc.groups.size());
     }
     const int S = (int)c->shapes.size();
 
@@ -452,7 +468,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
             float2* scr = nullptr;
             CK(dalloc(&scr, (size_t)gplan.M));
             SectionGeom Gr{cl.d_rev, 0, L, L, 0, 0};
-            launch_forward(gplan, Gr, nullptr, 0, 1, scr, cl.d_spec, gplan.M, 0);
+            launch_forward(gplan, Gr, FwdGroups{nullptr, nullptr, nullptr, 0}, nullptr, 0, 1, scr, cl.d_spec, gplan.M, 0);
             CK(cudaDeviceSynchronize());
             cudaFree(scr);
             c->launches += 2;
@@ -578,7 +594,8 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     c->n_slots = 256;
     c->inv_units = 512;
     if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
-    c->scratch_elems = std::max<long long>(std::max<long long>(B, c->inv_units), c->n_slots) * max_M;
+    c->scratch_elems = std::max<long long>(std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units),
+                                           c->n_slots) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
     CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(std::max(c->inv_units, c->n_slots))));
     CK(dalloc(&c->d_unit_max, (size_t)B * n_clips));
@@ -631,7 +648,10 @@ extern "C" int apd_destroy(apd_ctx* c)
         cudaFree(cl.d_self_corr); cudaFree(cl.d_win_cache); cudaFree(cl.d_tone_chirp); cudaFree(cl.d_tone_tw);
         cudaFree(cl.d_tone_pre); cudaFree(cl.d_tone_post);
     }
-    for (auto& sc : c->shapes) { free_plan(&sc.plan); cudaFree(sc.d_clips); }
+    for (auto& sc : c->shapes) {
+        free_plan(&sc.plan);
+        cudaFree(sc.d_clips); cudaFree(sc.d_group_halo); cudaFree(sc.d_group_index); cudaFree(sc.d_group_spec_off);
+    }
     for (auto& kv : c->self_plans) free_plan(&kv.second);
     kw_config_destroy(&c->kw);
     void* ptrs[] = {c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
@@ -717,11 +737,20 @@ static int stage_loudness(apd_ctx* c, cudaStream_t st)
 static int stage_forward(apd_ctx* c, cudaStream_t st)
 {
     const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size();
-    for (int g = 0; g < G; ++g) {
-        Group& gr = c->groups[g];
-        launch_forward(c->shapes[gr.shape].plan, c->h_geoms[g], c->d_gain + g, G, B, c->d_scratch,
-                       c->d_spec + gr.spec_off, c->spec_slab, st);
-        c->launches += 2;
+    for (auto& sc : c->shapes) {
+        if (corr_inv_supported(sc.plan)) {
+            // all sliding-window groups of the shape in one pair of launches
+            FwdGroups FG{sc.d_group_halo, sc.d_group_index, sc.d_group_spec_off, (int)sc.groups.size()};
+            launch_forward(sc.plan, c->h_geoms[sc.groups[0]], FG, c->d_gain, G, B, c->d_scratch, c->d_spec,
+                           c->spec_slab, st);
+            c->launches += 2;
+            continue;
+        }
+        for (int g : sc.groups) {
+            launch_forward(sc.plan, c->h_geoms[g], FwdGroups{nullptr, nullptr, nullptr, 0}, c->d_gain + g, G, B,
+                           c->d_scratch, c->d_spec + c->groups[g].spec_off, c->spec_slab, st);
+            c->launches += 2;
+        }
     }
     CK(cudaGetLastError());
     return APD_OK;

@@ -55,30 +55,6 @@ __global__ void k_unit_desc(UnitSrc U, UnitCtx C, const float2* __restrict__ spe
     D[u] = d;
 }
 
-// ---------------------------------------------------------------- shared-memory access by 32-bit address
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-template <int OFF> __device__ __forceinline__ c2 lds(unsigned a)
-{
-    c2 r;
-    asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(r.v) : "r"(a), "n"(OFF) : "memory");
-    return r;
-}
-__device__ __forceinline__ void sts(unsigned a, c2 v)
-{
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v.v) : "memory");
-}
-__device__ __forceinline__ c2 ldg_nc(const c2* p)          // read-only path, keeps the line in L1
-{
-    c2 r;
-    r.v = __ldg(reinterpret_cast<const unsigned long long*>(p));
-    return r;
-}
-__device__ __forceinline__ c2 ldg_stream(const c2* p)      // streamed once: do not pollute L1
-{
-    c2 r;
-    asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(r.v) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ UnitDesc load_desc(const UnitDesc* p)
 {
     UnitDesc d;
@@ -182,12 +158,7 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
 }
 
 // ---------------------------------------------------------------- columns
-// TB = 4 adjacent columns on the lanes (q = tid % 4), butterfly j = tid / 4; N1 = R0 R1 R2 = 8*8*8 or
-// 8*8*10.  Exchange layout: word(e, q) = 4 * (e ^ ((e >> 3) & 3)) + q.
-//   loads  e = j + T r  (T = N1/8 in pass 2, 64 in pass 3): 32 (j ^ s) + 8 q + 32 T r, s = (j >> 3) & 3,
-//          and for T = 80 odd r use s ^ 2                                    (constant + immediate)
-//   stores e = 8 j + r (pass 1)                    : (32 (8 j + (j & 3)) + 8 q) ^ (32 r)
-//   stores e = 64 (j >> 3) + (j & 7) + 8 r (pass 2): (32 (64 (j >> 3) + (j & 7)) + 8 q) ^ (32 (8 r + (r & 3)))
+// kTB adjacent columns on the lanes; exchange layout and address forms: ColAddr / ColLoad (fft_fast.cuh).
 constexpr int kTB = 4;
 
 // e^{i pi r / (2 R)}, r < R: the r-dependent part of the post-twiddle (immediates after unrolling)
@@ -204,11 +175,6 @@ __device__ __forceinline__ float2 post_const10(int r)
     return make_float2(c[r], s[r]);
 }
 
-template <int OFF> __device__ __forceinline__ c2 lds_sel(unsigned a0, unsigned a1, bool odd)
-{
-    return odd ? lds<OFF>(a1) : lds<OFF>(a0);
-}
-
 template <class S, bool WRITE>
 __global__ void __launch_bounds__(kTB * (S::N / 8), S::N == 512 ? 3 : 2)
 k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
@@ -219,18 +185,12 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
     constexpr int R2 = S::R2;             // last radix: 8 or 10
     constexpr int NLAST = N1 / R2;        // 64 butterflies in the last pass
     constexpr int NW = kTB * T1 / 32;     // warps per CTA
-    // the store addresses are formed as (constant ^ immediate) with immediates up to 2^11: the buffer base
-    // must be 2 KB aligned, which is more than a static __shared__ declaration guarantees
-    __shared__ __align__(1024) c2 raw[N1 * kTB + 128];
+    __shared__ __align__(1024) c2 raw[N1 * kTB + ColLayout<kTB>::SLACK];
     __shared__ float red[NW];
     const int q = threadIdx.x % kTB, j = threadIdx.x / kTB;
     const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
     const int bcol = bx * kTB + q;
-    const unsigned sb = ((smem_addr(raw) + 2047u) & ~2047u) + 8u * (unsigned)q;
-    const unsigned ld_a = sb + 32u * (unsigned)(j ^ ((j >> 3) & 3));                 // even r (and all r if T = 64)
-    const unsigned ld_b = sb + 32u * (unsigned)(j ^ (((j >> 3) & 3) ^ 2));           // odd r when T = 80
-    const unsigned st1 = sb + 32u * (unsigned)(8 * j + (j & 3));
-    const unsigned st2 = sb + 32u * (unsigned)(64 * (j >> 3) + (j & 7));
+    const ColAddr<kTB> A(raw, j, q);
     float2 tw2[8], tw3[R2];
     pass_twiddles<8, +1, 8>(j, tw2);
     pass_twiddles<R2, +1, 64>(j, tw3);
@@ -256,27 +216,17 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
 #pragma unroll
         for (int r = 0; r < 8; ++r) v[r] = ldg_stream(in + (long long)T1 * kN2 * r);
         Dft2<8, +1>::run(v);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) sts(st1 ^ (32u * r), v[r]);
+        col_store1<kTB>(A, v);
         __syncthreads();
-        if (N1 == 512) {
-            v[0] = lds<0>(ld_a); v[1] = lds<32 * 64 * 1>(ld_a); v[2] = lds<32 * 64 * 2>(ld_a); v[3] = lds<32 * 64 * 3>(ld_a);
-            v[4] = lds<32 * 64 * 4>(ld_a); v[5] = lds<32 * 64 * 5>(ld_a); v[6] = lds<32 * 64 * 6>(ld_a); v[7] = lds<32 * 64 * 7>(ld_a);
-        } else {
-            v[0] = lds<0>(ld_a); v[1] = lds<32 * 80 * 1>(ld_b); v[2] = lds<32 * 80 * 2>(ld_a); v[3] = lds<32 * 80 * 3>(ld_b);
-            v[4] = lds<32 * 80 * 4>(ld_a); v[5] = lds<32 * 80 * 5>(ld_b); v[6] = lds<32 * 80 * 6>(ld_a); v[7] = lds<32 * 80 * 7>(ld_b);
-        }
+        ColLoad<kTB, T1, 8>::run(A, v);
         __syncthreads();
         bfly_tw<8>(v, tw2);
         Dft2<8, +1>::run(v);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) sts(st2 ^ (32u * (8 * r + (r & 3))), v[r]);
+        col_store2<kTB>(A, v);
         __syncthreads();
         float best = 0.0f;
         if (N1 == 512 || j < NLAST) {
-            v[0] = lds<0>(ld_a); v[1] = lds<32 * 64 * 1>(ld_a); v[2] = lds<32 * 64 * 2>(ld_a); v[3] = lds<32 * 64 * 3>(ld_a);
-            v[4] = lds<32 * 64 * 4>(ld_a); v[5] = lds<32 * 64 * 5>(ld_a); v[6] = lds<32 * 64 * 6>(ld_a); v[7] = lds<32 * 64 * 7>(ld_a);
-            if (R2 == 10) { v[8] = lds<32 * 64 * 8>(ld_a); v[9] = lds<32 * 64 * 9>(ld_a); }
+            ColLoad<kTB, 64, R2>::run(A, v);
 #pragma unroll
             for (int r = 0; r < R2; ++r) v[r] = cmul(v[r], tw3[r]);
             Dft2<R2, +1>::run(v);

@@ -213,7 +213,7 @@ __device__ __forceinline__ c2 ldg_c2(const c2* p)
 template <int TR>
 __global__ void __launch_bounds__(TR * 64)
 k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ spec, long long spec_stride,
-                int nsec, int per)
+                FwdGroups FG, int ntr, int per)
 {
     __shared__ c2 buf[TR * kRowPitch];
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
@@ -222,9 +222,11 @@ k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ s
     float2 tw2[8], tw3[8];
     pass_twiddles<8, -1, 8>(j, tw2);
     pass_twiddles<8, -1, 64>(j, tw3);
-    const int s_end = min(nsec, (int)(blockIdx.y + 1) * per);
-    for (int sec = blockIdx.y * per; sec < s_end; ++sec) {
-        const c2* __restrict__ in = reinterpret_cast<const c2*>(T + (long long)sec * P.M + (long long)c * kRowN);
+    const int t_end = min(ntr, (int)(blockIdx.y + 1) * per);
+    for (int t = blockIdx.y * per; t < t_end; ++t) {
+        const int sec = FG.ng ? t / FG.ng : t;
+        const long long goff = FG.ng ? FG.spec_off[t - sec * FG.ng] : 0;
+        const c2* __restrict__ in = reinterpret_cast<const c2*>(T + (long long)t * P.M + (long long)c * kRowN);
         c2 v[8];
         bfly_ld<8, kRowN>(j, [&](int e) { return in[e]; }, v);
         Dft2<8, -1>::run(v);
@@ -240,68 +242,82 @@ k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ s
         group_sync<64>(q + 1);
         bfly_tw<8>(v, tw3);
         Dft2<8, -1>::run(v);
-        c2* __restrict__ out = reinterpret_cast<c2*>(spec + (long long)sec * spec_stride + (long long)c * kRowN);
+        c2* __restrict__ out = reinterpret_cast<c2*>(spec + (long long)sec * spec_stride + goff + (long long)c * kRowN);
 #pragma unroll
         for (int r = 0; r < 8; ++r) out[j + 64 * r] = v[r];
     }
 }
 
-// Column kernels: S::N = N1, TB adjacent columns, threads = TB * (N1 / 8).
+// Column kernel: S::N = N1 = 8 * 8 * R2, TB adjacent columns on the lanes, threads = TB * (N1 / 8).
+// Fused with the section load: loudness gain, clamp, NaN scrub (lib.rs:220-227, apd.py:489-490), packing
+// u[m] = x[m] - i x[m + M] and the pre-twiddle e^{-i pi m / N}.  Exchange addressing: ColAddr / ColLoad.
 template <class S, int TB>
-__global__ void __launch_bounds__(TB * (S::N / 8))
-k_fwd_cols_fast(Fft4Plan P, SectionGeom G, const double* __restrict__ gains, int gain_stride, float2* __restrict__ T,
-                int nsec, int per)
+__global__ void __launch_bounds__(TB * (S::N / 8), (TB * (S::N / 8) <= 256) ? 3 : (TB * (S::N / 8) <= 320 ? 2 : 1))
+k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restrict__ gains, int gain_stride,
+                float2* __restrict__ T, int ntr, int per)
 {
     constexpr int N1 = S::N;
-    constexpr int NLAST = N1 / S::R2;
-    __shared__ c2 buf[N1 * TB];
+    constexpr int T1 = N1 / 8;
+    constexpr int R2 = S::R2;
+    constexpr int NLAST = N1 / R2;
+    __shared__ __align__(1024) c2 raw[N1 * TB + ColLayout<TB>::SLACK];
     const int q = threadIdx.x % TB, j = threadIdx.x / TB;
     const int bcol = blockIdx.x * TB + q;
-    const int M = P.M, N2 = P.N2;
-    float2 pre[S::R0], tw2[S::R1], tw3[S::R2], fs[S::R2];
+    const int M = P.M;
+    const ColAddr<TB> A(raw, j, q);
+    float2 pre[8], tw2[8], tw3[R2], fs[R2];
     {
-        // pre-twiddle e^{-i pi m / N}, m = (j + r N1/R0) N2 + b  = base * (e^{-i pi / (2 R0)})^r
+        // pre-twiddle e^{-i pi m / N}, m = (j + r N1/8) 512 + b  = base * (e^{-i pi / 16})^r
         const float invN = 1.0f / (2.0f * (float)M);
-        geometric<S::R0>(cispif(-(float)(j * N2 + bcol) * invN), cispif(-0.5f / (float)S::R0), pre);
-        pass_twiddles<S::R1, -1, S::R0>(j, tw2);
-        pass_twiddles<S::R2, -1, S::R0 * S::R1>(j, tw3);
+        geometric<8>(cispif(-(float)(j * kRowN + bcol) * invN), cispif(-0.5f / 8.0f), pre);
+        pass_twiddles<8, -1, 8>(j, tw2);
+        pass_twiddles<R2, -1, 64>(j, tw3);
         // outputs c = j + r * NLAST ; four-step twiddle w_M^{-b c} = base * step^r
         const float invM = 1.0f / (float)M;
-        geometric<S::R2>(twiddle_frac(bcol * (j % NLAST), invM, -1.0f), twiddle_frac(bcol * NLAST, invM, -1.0f), fs);
+        geometric<R2>(twiddle_frac(bcol * (j % NLAST), invM, -1.0f), twiddle_frac(bcol * NLAST, invM, -1.0f), fs);
     }
-    const int s_end = min(nsec, (int)(blockIdx.y + 1) * per);
-    for (int sec = blockIdx.y * per; sec < s_end; ++sec) {
+    const int m_lo = j * kRowN + bcol;                       // first-pass input r: m = m_lo + r * T1 * 512
+    const int t_end = min(ntr, (int)(blockIdx.y + 1) * per);
+    for (int t = blockIdx.y * per; t < t_end; ++t) {
+        const int sec = FG.ng ? t / FG.ng : t;
+        int gcol = 0;
+        if (FG.ng) {
+            const int gi = t - sec * FG.ng;
+            G.halo = FG.halo[gi];
+            gcol = FG.gain_index[gi];
+        }
         long long start;
         int n;
         section_bounds(G, sec, start, n);
-        const float* __restrict__ x = G.audio + (start - G.base);
-        const double gain = gains ? gains[(long long)sec * gain_stride] : 1.0;
-        c2 v[10];
-        bfly_ld<S::R0, N1>(j, [&](int e) {
-            const int m = e * N2 + bcol;
-            const float x0 = m < n ? normalize_sample(x[m], gain) : 0.0f;
-            const float x1 = m + M < n ? normalize_sample(x[m + M], gain) : 0.0f;
-            return mk(x0, -x1);
-        }, v);
+        const float* __restrict__ x = G.audio + (start - G.base) + m_lo;
+        const double gain = gains ? gains[(long long)sec * gain_stride + gcol] : 1.0;
+        c2 v[R2 > 8 ? R2 : 8];
+        float x0[8], x1[8];
 #pragma unroll
-        for (int r = 0; r < S::R0; ++r) v[r] = cmul(v[r], pre[r]);
-        Dft2<S::R0, -1>::run(v);
-        bfly_store<S::R0, 1>(j, [&](int e, c2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
-        __syncthreads();
-        bfly_ld<S::R1, N1>(j, [&](int e) { return buf[cswz<TB>(e) * TB + q]; }, v);
-        __syncthreads();
-        bfly_tw<S::R1>(v, tw2);
-        Dft2<S::R1, -1>::run(v);
-        bfly_store<S::R1, S::R0>(j, [&](int e, c2 y) { buf[cswz<TB>(e) * TB + q] = y; }, v);
-        __syncthreads();
-        if (j < NLAST) {
-            bfly_ld<S::R2, N1>(j, [&](int e) { return buf[cswz<TB>(e) * TB + q]; }, v);
-            bfly_tw<S::R2>(v, tw3);
-            Dft2<S::R2, -1>::run(v);
-            c2* __restrict__ out = reinterpret_cast<c2*>(T + (long long)sec * M);
+        for (int r = 0; r < 8; ++r) {
+            const int m = m_lo + r * T1 * kRowN;
+            x0[r] = m < n ? x[r * T1 * kRowN] : 0.0f;
+            x1[r] = m + M < n ? x[r * T1 * kRowN + M] : 0.0f;
+        }
 #pragma unroll
-            for (int r = 0; r < S::R2; ++r)
-                out[(long long)(j + r * NLAST) * N2 + bcol] = cmul(v[r], fs[r]);
+        for (int r = 0; r < 8; ++r)
+            v[r] = cmul(mk(normalize_sample(x0[r], gain), -normalize_sample(x1[r], gain)), pre[r]);
+        Dft2<8, -1>::run(v);
+        col_store1<TB>(A, v);
+        __syncthreads();
+        ColLoad<TB, T1, 8>::run(A, v);
+        __syncthreads();
+        bfly_tw<8>(v, tw2);
+        Dft2<8, -1>::run(v);
+        col_store2<TB>(A, v);
+        __syncthreads();
+        if (N1 == 512 || j < NLAST) {
+            ColLoad<TB, 64, R2>::run(A, v);
+            bfly_tw<R2>(v, tw3);
+            Dft2<R2, -1>::run(v);
+            c2* __restrict__ out = reinterpret_cast<c2*>(T + (long long)t * M + (long long)j * kRowN + bcol);
+#pragma unroll
+            for (int r = 0; r < R2; ++r) out[(long long)r * NLAST * kRowN] = cmul(v[r], fs[r]);
         }
         __syncthreads();
     }
@@ -315,7 +331,7 @@ static int env_int(const char* name, int dflt)
     return e ? atoi(e) : dflt;
 }
 // tuning knobs (defaults chosen on B200; overridable for experiments)
-static int fast_tb() { static int v = env_int("APD_B200_TB", 4) == 8 ? 8 : 4; return v; }      // columns per CTA
+static int fast_tb() { static int v = env_int("APD_B200_TB", 8) == 4 ? 4 : 8; return v; }      // columns per forward CTA
 static int fast_per_max() { static int v = std::max(1, env_int("APD_B200_PER", 8)); return v; }  // transforms per CTA
 
 static int fast_per(int n)
@@ -327,14 +343,15 @@ static int fast_per(int n)
 }
 
 template <int TB>
-static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G, const double* gains, int gain_stride,
-                                 float2* scratch, int nsec, int per, int ny, cudaStream_t st)
+static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G, const FwdGroups& FG,
+                                 const double* gains, int gain_stride, float2* scratch, int ntr, int per, int ny,
+                                 cudaStream_t st)
 {
     dim3 gc(P.N2 / TB, ny);
     if (fs == 512)
-        k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, 0, st>>>(P, G, gains, gain_stride, scratch, nsec, per);
+        k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, 0, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
     else
-        k_fwd_cols_fast<Shape640, TB><<<gc, TB * 80, 0, st>>>(P, G, gains, gain_stride, scratch, nsec, per);
+        k_fwd_cols_fast<Shape640, TB><<<gc, TB * 80, 0, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
 }
 
 static int fast_shape(const Fft4Plan& P)
@@ -454,20 +471,28 @@ static void ensure_attrs()
     done = true;
 }
 
-void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains, int gain_stride, int nsec,
-                    float2* scratch, float2* spec, long long spec_stride, cudaStream_t st)
+void launch_forward(const Fft4Plan& P, const SectionGeom& G, const FwdGroups& FG, const double* gains, int gain_stride,
+                    int nsec, float2* scratch, float2* spec, long long spec_stride, cudaStream_t st)
 {
     if (nsec <= 0) return;
     ensure_attrs();
     const int fs = fast_shape(P);
     if (fs) {
-        const int per = fast_per(nsec), ny = (nsec + per - 1) / per;
-        dim3 gr(P.N1 / kFastTR, ny);
-        if (fast_tb() == 8) launch_fwd_cols_fast<8>(fs, P, G, gains, gain_stride, scratch, nsec, per, ny, st);
-        else launch_fwd_cols_fast<4>(fs, P, G, gains, gain_stride, scratch, nsec, per, ny, st);
-        k_fwd_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, scratch, spec, spec_stride, nsec, per);
+        const int ntr = nsec * std::max(FG.ng, 1);
+        const int tb = fast_tb();
+        // keep >= ~4 CTAs per SM in the grid, otherwise amortise the twiddle set-up over many transforms
+        int per = std::max(fast_per_max(), 32);
+        while (per > 1 && (long long)((ntr + per - 1) / per) * (P.N2 / tb) < 148 * 4) per >>= 1;
+        const int ny = (ntr + per - 1) / per;
+        if (tb == 8) launch_fwd_cols_fast<8>(fs, P, G, FG, gains, gain_stride, scratch, ntr, per, ny, st);
+        else launch_fwd_cols_fast<4>(fs, P, G, FG, gains, gain_stride, scratch, ntr, per, ny, st);
+        int perr = std::max(fast_per_max(), 32);
+        while (perr > 1 && (long long)((ntr + perr - 1) / perr) * (P.N1 / kFastTR) < 148 * 8) perr >>= 1;
+        dim3 gr(P.N1 / kFastTR, (ntr + perr - 1) / perr);
+        k_fwd_rows_fast<kFastTR><<<gr, kFastTR * 64, 0, st>>>(P, scratch, spec, spec_stride, FG, ntr, perr);
         return;
     }
+    // generic shapes: one group per launch (FG.ng == 0)
     dim3 gc(P.N2 >> P.tb_log2, nsec), gr(P.N1 >> P.tr_log2, nsec);
     k_fwd_cols<<<gc, P.threads, P.smem_col, st>>>(P, G, gains, gain_stride, scratch);
     k_fwd_rows<<<gr, P.threads, P.smem_row, st>>>(P, scratch, spec, spec_stride);

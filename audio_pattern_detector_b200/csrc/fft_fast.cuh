@@ -174,4 +174,85 @@ __device__ __forceinline__ void group_sync(int id)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory");
 }
 
+// ---------------------------------------------------------------- shared-memory access by 32-bit address
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF> __device__ __forceinline__ c2 lds(unsigned a)
+{
+    c2 r;
+    asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(r.v) : "r"(a), "n"(OFF) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts(unsigned a, c2 v)
+{
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v.v) : "memory");
+}
+__device__ __forceinline__ c2 ldg_nc(const c2* p)          // read-only path, keeps the line in L1
+{
+    c2 r;
+    r.v = __ldg(reinterpret_cast<const unsigned long long*>(p));
+    return r;
+}
+__device__ __forceinline__ c2 ldg_stream(const c2* p)      // streamed once: do not pollute L1
+{
+    c2 r;
+    asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(r.v) : "l"(p));
+    return r;
+}
+
+// Column-kernel exchange layout: TB adjacent columns on the lanes (q = tid % TB), butterfly j = tid / TB,
+// word(e, q) = TB * (e ^ ((e >> 3) & SW)) + q with SW = 3 (TB = 4) or 1 (TB = 8); N1 = 8 * 8 * R2.
+//   loads  e = j + T r (T = N1/8 in pass 2, 64 in pass 3): 8 TB (j ^ s) + 8 q + 8 TB T r, s = (j >> 3) & SW;
+//          for T = 80 and SW = 3 odd r use s ^ 2                                   (constant + immediate)
+//   stores e = 8 j + r (pass 1)                    : (8 TB (8 j + (j & SW)) + 8 q) ^ (8 TB r)
+//   stores e = 64 (j >> 3) + (j & 7) + 8 r (pass 2): (8 TB (64 (j >> 3) + (j & 7)) + 8 q) ^ (8 TB (8 r + (r & SW)))
+// The (constant ^ immediate) form needs the buffer base aligned to 8 TB 64 bytes; col_buffer_base()
+// rounds a 1 KB aligned static buffer (declared with kColSlack extra elements) up to that.
+template <int TB> struct ColLayout {
+    static constexpr int SW = TB == 8 ? 1 : 3;
+    static constexpr unsigned ALIGN = 8u * TB * 64u;
+    static constexpr int SLACK = (int)(ALIGN / 8u);        // extra c2 elements to declare
+};
+
+template <int TB>
+struct ColAddr {
+    unsigned ld_a, ld_b, st1, st2;
+    __device__ __forceinline__ ColAddr(const void* raw, int j, int q)
+    {
+        constexpr int SW = ColLayout<TB>::SW;
+        constexpr unsigned AL = ColLayout<TB>::ALIGN;
+        const unsigned sb = ((smem_addr(raw) + AL - 1u) & ~(AL - 1u)) + 8u * (unsigned)q;
+        const int s = (j >> 3) & SW;
+        ld_a = sb + 8u * TB * (unsigned)(j ^ s);
+        ld_b = sb + 8u * TB * (unsigned)(j ^ ((s + 2) & SW));
+        st1 = sb + 8u * TB * (unsigned)(8 * j + (j & SW));
+        st2 = sb + 8u * TB * (unsigned)(64 * (j >> 3) + (j & 7));
+    }
+};
+
+// v[r] = exchange[j + T r], r < R
+template <int TB, int T, int R> struct ColLoad {
+    template <int r> static __device__ __forceinline__ c2 one(const ColAddr<TB>& A)
+    {
+        // ((j >> 3) + (T / 8) r) & SW differs from (j >> 3) & SW only for T = 80, SW = 3, odd r
+        constexpr bool alt = (T == 80) && (ColLayout<TB>::SW == 3) && (r & 1);
+        return lds<8 * TB * T * r>(alt ? A.ld_b : A.ld_a);
+    }
+    static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* v)
+    {
+        v[0] = one<0>(A); v[1] = one<1>(A); v[2] = one<2>(A); v[3] = one<3>(A);
+        v[4] = one<4>(A); v[5] = one<5>(A); v[6] = one<6>(A); v[7] = one<7>(A);
+        if (R == 10) { v[8] = one<8>(A); v[9] = one<9>(A); }
+    }
+};
+template <int TB> __device__ __forceinline__ void col_store1(const ColAddr<TB>& A, const c2* v)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sts(A.st1 ^ (8u * TB * r), v[r]);
+}
+template <int TB> __device__ __forceinline__ void col_store2(const ColAddr<TB>& A, const c2* v)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sts(A.st2 ^ (8u * TB * (8 * r + (r & ColLayout<TB>::SW))), v[r]);
+}
+
 }  // namespace apd

@@ -89,8 +89,18 @@ bool build_plan(int M_min, Fft4Plan* plan, std::string* err);                 //
 void free_plan(Fft4Plan* plan);
 long long plan_min_M_for(long long n_out);
 
-void launch_forward(const Fft4Plan& P, const SectionGeom& G, const double* gains, int gain_stride, int nsec,
-                    float2* scratch /* nsec*M */, float2* spec, long long spec_stride, cudaStream_t st);
+// The sliding-window groups of one FFT shape, transformed by the same launches (device arrays of ng entries):
+// transform t of a launch is section t / ng of group t % ng, so the groups of a chunk re-read its audio from L2.
+struct FwdGroups {
+    const int* halo;             // look-back samples of each group
+    const int* gain_index;       // column of the gain matrix (global group id)
+    const long long* spec_off;   // offset of the group's spectrum inside a chunk's slab
+    int ng;                      // 0: a single group described by G.halo, gain column 0, offset 0
+};
+
+// scratch holds nsec * max(ng, 1) * M complex; spectra go to spec + section * spec_stride + spec_off[group].
+void launch_forward(const Fft4Plan& P, const SectionGeom& G, const FwdGroups& FG, const double* gains, int gain_stride,
+                    int nsec, float2* scratch, float2* spec, long long spec_stride, cudaStream_t st);
 // Fused spectral multiply + inverse FFT + |.| ; write == false: per-unit max, write == true: normalised
 // correlation into O.corr.  scratch holds nunits * M complex (launch-local unit index).
 // desc: device scratch of corr_inv_desc_bytes(nunits) bytes (per-unit descriptors of the hot-shape kernels).
