@@ -183,6 +183,7 @@ class AudioPatternDetector:
         self._max_halo = max(self._sliding_windows, default=0) * sr
         self._dev_buf = None
         self._pinned = None
+        self._cand_buf = None
 
     # ------------------------------------------------------------------ helpers
     def _fallback_tone_frequency(self, raw: NDArray[np.float32]) -> Optional[float]:
@@ -259,7 +260,10 @@ class AudioPatternDetector:
         nb = chunk_end - chunk_begin
         ncl = len(self.audio_clips)
         cap = max(4096, nb * ncl * 4)
-        cands = (_lib.Candidate * cap)()
+        if self._cand_buf is None or len(self._cand_buf) < cap:
+            self._cand_buf = (_lib.Candidate * cap)()
+        cands = self._cand_buf
+        cap = len(cands)
         n = C.c_int32(0)
         trace = (_lib.UnitTrace * (nb * ncl))() if want_trace else None
         lufs = (C.c_double * (nb * ncl))() if want_trace else None
@@ -321,10 +325,18 @@ class AudioPatternDetector:
         the global chunk indices this call scans and ``total_samples`` the length of the whole
         stream (only its final chunk is shorter)."""
         torch = _torch()
+        devname = f"cuda:{self._device}"
+        host = None
         if isinstance(audio, np.ndarray):
-            dev = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(f"cuda:{self._device}")
-        else:   # torch tensor: CUDA (used in place) or host (pinned host memory copies at full PCIe rate)
-            dev = audio.to(device=f"cuda:{self._device}", dtype=torch.float32, non_blocking=True).contiguous()
+            host = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
+        elif not audio.is_cuda:
+            host = audio.to(dtype=torch.float32).contiguous()
+        if host is not None:
+            # host input: copied segment by segment on a copy stream, overlapped with the scan of the
+            # previous segment (pinned host memory copies at full PCIe rate)
+            dev = torch.empty(host.numel(), dtype=torch.float32, device=devname)
+        else:
+            dev = audio.to(device=devname, dtype=torch.float32).contiguous()
         n = dev.numel()
         C_ = self._chunk_samples
         end_sample = base_sample + n                    # one past the last stream sample held
@@ -341,8 +353,33 @@ class AudioPatternDetector:
         all_cands: list[Candidate] = []
         trace: Optional[dict] = {} if collect_trace else None
         with torch.cuda.device(self._device):
-            for c0 in range(first, last, self._max_batch):
-                c1 = min(last, c0 + self._max_batch)
+            # one apd_scan per segment: the C side cuts a segment into sub-batches of max_batch_chunks chunks
+            # and overlaps phase 2 of one sub-batch with phase 1 of the next
+            seg = self._max_batch * 8 if host is not None else max(last - first, 1)
+            bounds = list(range(first, last, seg)) + [last]
+            copied = 0                                   # slab samples already enqueued for copy
+            copy_stream = torch.cuda.Stream() if host is not None else None
+            ready: list[Any] = []
+
+            def enqueue_copy(upto_chunk: int) -> None:
+                nonlocal copied
+                hi = min(n, upto_chunk * C_ - base_sample)
+                if hi > copied:
+                    with torch.cuda.stream(copy_stream):
+                        dev[copied:hi].copy_(host[copied:hi], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    ready.append(ev)
+                    copied = hi
+
+            if host is not None and len(bounds) > 1:
+                enqueue_copy(bounds[1])
+            for si in range(len(bounds) - 1):
+                c0, c1 = bounds[si], bounds[si + 1]
+                if host is not None:
+                    torch.cuda.current_stream().wait_event(ready[si])
+                    if si + 2 < len(bounds):
+                        enqueue_copy(bounds[si + 2])
                 cands, tr = self._scan_batch(dev.data_ptr(), base_sample, n, c0, c1, collect_trace)
                 all_cands.extend(cands)
                 if trace is not None and tr:

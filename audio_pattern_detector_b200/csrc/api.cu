@@ -242,9 +242,29 @@ struct apd_ctx {
     void* d_tone_items = nullptr;
     double* d_tone_metrics = nullptr;
 
-    // optional stage timing (CUDA events on the caller's stream)
+    // phase 2 (selected units only) runs on a side stream, overlapped with phase 1 of the next sub-batch:
+    // it has its own four-step scratch / descriptors, and everything phase 1 hands over to it is
+    // double-buffered (BatchSet below; the pointers above are those of the set in use).
+    float2* d_scratch2 = nullptr;
+    void* d_unit_desc2 = nullptr;
+    cudaStream_t side = nullptr;
+    struct BatchSet {
+        float2* d_spec = nullptr;
+        unsigned int* d_unit_max = nullptr;
+        int* d_unit_npeaks = nullptr;
+        int *d_counts = nullptr, *h_counts = nullptr;
+        int2* d_sel = nullptr;
+        double *d_lufs = nullptr, *d_gain = nullptr;
+        SectionGeom *d_geoms = nullptr, *h_geoms = nullptr;
+        int chunk_begin = 0, chunk_end = 0;
+        cudaEvent_t p1_done = nullptr;
+        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    } sets[2];
+    int cur_set = 0;
+
+    // optional stage timing (CUDA events: [0..3] on the caller's stream, [4..5] on the side stream)
     bool profile = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t* ev = nullptr;
     double stage_ms[4] = {0, 0, 0, 0};
 
     // state of the staged batch
@@ -253,6 +273,20 @@ struct apd_ctx {
     int chunk_begin = 0, chunk_end = 0;
     bool staged = false;
 };
+
+static void use_set(apd_ctx* c, int k)
+{
+    apd_ctx::BatchSet& cur = c->sets[c->cur_set];
+    cur.chunk_begin = c->chunk_begin;
+    cur.chunk_end = c->chunk_end;
+    apd_ctx::BatchSet& b = c->sets[k];
+    c->d_spec = b.d_spec; c->d_unit_max = b.d_unit_max; c->d_unit_npeaks = b.d_unit_npeaks;
+    c->d_counts = b.d_counts; c->h_counts = b.h_counts; c->d_sel = b.d_sel;
+    c->d_lufs = b.d_lufs; c->d_gain = b.d_gain; c->d_geoms = b.d_geoms; c->h_geoms = b.h_geoms;
+    c->chunk_begin = b.chunk_begin; c->chunk_end = b.chunk_end;
+    c->ev = b.ev;
+    c->cur_set = k;
+}
 
 static void fill_geoms(apd_ctx* c)
 {
@@ -579,8 +613,10 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
 
     // ---- workspace
     const int B = c->maxB;
-    CK(dalloc(&c->d_geoms, (size_t)G));
-    CK(cudaMallocHost((void**)&c->h_geoms, sizeof(SectionGeom) * G));
+    for (auto& b : c->sets) {
+        CK(dalloc(&b.d_geoms, (size_t)G));
+        CK(cudaMallocHost((void**)&b.h_geoms, sizeof(SectionGeom) * G));
+    }
     long long max_sec = c->C;
     for (auto& g : c->groups) max_sec = std::max(max_sec, c->C + g.halo);
     c->cells_stride = (int)((max_sec + c->kw.cell - 1) / c->kw.cell + 1);
@@ -588,22 +624,31 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(dalloc(&c->d_kw_energy, (size_t)B * c->cells_stride));
     CK(dalloc(&c->d_kw_em1, (size_t)B));
     CK(dalloc(&c->d_kw_patch, (size_t)B * G * c->kw.patch_cells));
-    CK(dalloc(&c->d_lufs, (size_t)B * G));
-    CK(dalloc(&c->d_gain, (size_t)B * G));
-    CK(dalloc(&c->d_spec, (size_t)B * c->spec_slab));
+    for (auto& b : c->sets) {
+        CK(dalloc(&b.d_lufs, (size_t)B * G));
+        CK(dalloc(&b.d_gain, (size_t)B * G));
+        CK(dalloc(&b.d_spec, (size_t)B * c->spec_slab));
+    }
     c->n_slots = 256;
     c->inv_units = 512;
     if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
-    c->scratch_elems = std::max<long long>(std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units),
-                                           c->n_slots) * max_M;
+    c->scratch_elems = std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
-    CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(std::max(c->inv_units, c->n_slots))));
-    CK(dalloc(&c->d_unit_max, (size_t)B * n_clips));
-    CK(dalloc(&c->d_unit_npeaks, (size_t)B * n_clips));
-    CK(dalloc(&c->d_counts, (size_t)S + 4));
-    CK(cudaMallocHost((void**)&c->h_counts, sizeof(int) * (S + 4)));
+    CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(c->inv_units)));
+    CK(dalloc(&c->d_scratch2, (size_t)c->n_slots * max_M));
+    CK(cudaMalloc(&c->d_unit_desc2, corr_inv_desc_bytes(c->n_slots)));
     c->sel_capacity = B * n_clips;
-    CK(dalloc(&c->d_sel, (size_t)c->sel_capacity));
+    for (auto& b : c->sets) {
+        CK(dalloc(&b.d_unit_max, (size_t)B * n_clips));
+        CK(dalloc(&b.d_unit_npeaks, (size_t)B * n_clips));
+        CK(dalloc(&b.d_counts, (size_t)S + 4));
+        CK(cudaMallocHost((void**)&b.h_counts, sizeof(int) * (S + 4)));
+        CK(dalloc(&b.d_sel, (size_t)c->sel_capacity));
+        CK(cudaEventCreateWithFlags(&b.p1_done, cudaEventDisableTiming));
+    }
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    c->cur_set = 0;
+    use_set(c, 0);
     c->corr_stride = (max_nout + 31) / 32 * 32;
     c->cand_stride = max_nout / 2 + 2;
     c->peak_stride = (int)std::min<long long>(max_nout / std::max(min_L, 1) + 2, 8192);
@@ -654,21 +699,27 @@ extern "C" int apd_destroy(apd_ctx* c)
     }
     for (auto& kv : c->self_plans) free_plan(&kv.second);
     kw_config_destroy(&c->kw);
-    void* ptrs[] = {c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
+    for (auto& b : c->sets) {
+        void* sp[] = {b.d_spec, b.d_unit_max, b.d_unit_npeaks, b.d_counts, b.d_sel, b.d_lufs, b.d_gain, b.d_geoms};
+        for (void* q : sp) cudaFree(q);
+        cudaFreeHost(b.h_counts);
+        cudaFreeHost(b.h_geoms);
+        if (b.p1_done) cudaEventDestroy(b.p1_done);
+        for (auto& e : b.ev)
+            if (e) cudaEventDestroy(e);
+    }
+    if (c->side) cudaStreamDestroy(c->side);
+    void* ptrs[] = {c->d_scratch2, c->d_unit_desc2,
+                    c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
                     c->d_win_ds, c->d_tone_P, c->d_self_max, (void*)c->d_self_corr_ptrs, (void*)c->d_win_cache_ptrs,
                     (void*)c->d_clip_spec_ptrs, c->d_tone_hz, c->d_tone_thr, (void*)c->d_tone_chirp_ptrs,
                     (void*)c->d_tone_tw_ptrs, (void*)c->d_tone_pre_ptrs, (void*)c->d_tone_post_ptrs, c->d_peak_height,
-                    c->d_clip_spec_off, c->d_sel, c->d_kw_patch,
-                    c->d_geoms, c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_lufs,
-                    c->d_gain, c->d_spec, c->d_scratch, c->d_unit_max, c->d_unit_npeaks, c->d_counts, c->d_corr,
+                    c->d_clip_spec_off, c->d_kw_patch,
+                    c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_scratch, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
                     c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics, c->d_tone_stats,
                     c->d_unit_desc};
     for (void* p : ptrs) cudaFree(p);
-    cudaFreeHost(c->h_geoms);
-    cudaFreeHost(c->h_counts);
-    for (int i = 0; i < 5; ++i)
-        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
     return APD_OK;
 }
@@ -785,7 +836,7 @@ static void phase2_round(apd_ctx* c, int slot0, cudaStream_t st)
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
     for (int s = 0; s < S; ++s) {
         UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0, 0};
-        launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch, c->d_unit_desc, O, true, st);
+        launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch2, c->d_unit_desc2, O, true, st);
         c->launches += 3;
     }
     PeakArgs PA{c->d_sel, c->d_counts + S, slot0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
@@ -871,6 +922,8 @@ static bool cand_less(const apd_candidate& a, const apd_candidate& b)
     return a.peak < b.peak;
 }
 
+// Finish phase 2 of the batch in the current set on stream st: further rounds if more than n_slots units were
+// selected, the deferred tone verification, then results to host.  Appends to cand_host[*n_cand ...].
 static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
                    double* lufs_host, cudaStream_t st)
 {
@@ -883,15 +936,16 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         CK(cudaStreamSynchronize(st));
     }
     phase2_tone(c, c->h_counts[S + 3], st);
-    if (c->profile) cudaEventRecord(c->ev[4], st);
+    if (c->profile) cudaEventRecord(c->ev[5], st);
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int n = c->h_counts[S + 1];
     if (c->h_counts[S + 2]) return fail(APD_ERR_OVERFLOW, "candidate workspace overflow (flags " +
                                         std::to_string(c->h_counts[S + 2]) + ")");
-    if (n > cap) return fail(APD_ERR_OVERFLOW, "candidate buffer too small");
+    if (*n_cand + n > cap) return fail(APD_ERR_OVERFLOW, "candidate buffer too small");
+    apd_candidate* dst = cand_host + *n_cand;
     if (n > 0) {
-        CK(cudaMemcpyAsync(cand_host, c->d_out, sizeof(apd_candidate) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(dst, c->d_out, sizeof(apd_candidate) * n, cudaMemcpyDeviceToHost, st));
     }
     std::vector<unsigned int> um;
     std::vector<int> np;
@@ -907,8 +961,8 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         CK(cudaMemcpyAsync(lf.data(), c->d_lufs, sizeof(double) * lf.size(), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
-    std::sort(cand_host, cand_host + n, cand_less);
-    *n_cand = n;
+    std::sort(dst, dst + n, cand_less);
+    *n_cand += n;
     if (trace) {
         for (int ci = 0; ci < B; ++ci)
             for (int p = 0; p < c->n_clips; ++p) {
@@ -928,33 +982,67 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         for (int ci = 0; ci < B; ++ci)
             for (int p = 0; p < c->n_clips; ++p)
                 lufs_host[(size_t)ci * c->n_clips + p] = lf[(size_t)ci * G + c->clips[p].group];
+    if (c->profile) {
+        for (int i = 0; i < 3; ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->stage_ms[i] += ms;
+        }
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->stage_ms[3] += ms;
+    }
     return APD_OK;
 }
 
+// Scan = for each sub-batch of at most max_batch_chunks chunks:
+//   phase 1 on the caller's stream : loudness -> forward FFT -> fused correlate + max          (all units)
+//   phase 2 on the side stream     : selection -> write-back inverse -> peaks -> verification  (selected units)
+// Phase 2 of sub-batch k overlaps phase 1 of sub-batch k + 1; what phase 1 hands over is double-buffered.
 extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n, int32_t cb, int32_t ce,
                         apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
                         double* lufs_host, void* stream)
 {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null output");
-    int rc = stage_begin(c, audio, base, n, cb, ce, st);
-    if (rc) return rc;
+    cudaStream_t s1 = (cudaStream_t)stream;
+    if (!c || !cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null argument");
+    if (ce <= cb) return fail(APD_ERR_INVALID, "scan: empty chunk range");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s2 = c->side;
+    *n_cand = 0;
+    const int nb = (ce - cb + c->maxB - 1) / c->maxB;
     const bool prof = c->profile;
-    if (prof) cudaEventRecord(c->ev[0], st);
-    if ((rc = stage_loudness(c, st))) return rc;
-    if (prof) cudaEventRecord(c->ev[1], st);
-    if ((rc = stage_forward(c, st))) return rc;
-    if (prof) cudaEventRecord(c->ev[2], st);
-    if ((rc = stage_correlate_max(c, st))) return rc;
-    if (prof) cudaEventRecord(c->ev[3], st);
-    if ((rc = stage_peaks_verify(c, st))) return rc;
-    rc = collect(c, cand_host, cap, n_cand, trace, lufs_host, st);
-    if (prof && rc == APD_OK) {
-        for (int i = 0; i < 4; ++i) {
-            float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->stage_ms[i] += ms;
-        }
+    int rc = APD_OK;
+    auto phase1 = [&](int k) -> int {
+        use_set(c, k & 1);
+        const int b0 = cb + k * c->maxB, b1 = std::min<int>(ce, b0 + c->maxB);
+        int r = stage_begin(c, audio, base, n, b0, b1, s1);
+        if (r) return r;
+        if (prof) cudaEventRecord(c->ev[0], s1);
+        if ((r = stage_loudness(c, s1))) return r;
+        if (prof) cudaEventRecord(c->ev[1], s1);
+        if ((r = stage_forward(c, s1))) return r;
+        if (prof) cudaEventRecord(c->ev[2], s1);
+        if ((r = stage_correlate_max(c, s1))) return r;
+        if (prof) cudaEventRecord(c->ev[3], s1);
+        CK(cudaEventRecord(c->sets[k & 1].p1_done, s1));
+        return APD_OK;
+    };
+    auto phase2_begin = [&](int k) -> int {
+        use_set(c, k & 1);
+        CK(cudaStreamWaitEvent(s2, c->sets[k & 1].p1_done, 0));
+        if (prof) cudaEventRecord(c->ev[4], s2);
+        return stage_peaks_verify(c, s2);
+    };
+    auto phase2_end = [&](int k) -> int {
+        use_set(c, k & 1);
+        const size_t off = (size_t)(c->chunk_begin - cb) * c->n_clips;
+        return collect(c, cand_host, cap, n_cand, trace ? trace + off : nullptr, lufs_host ? lufs_host + off : nullptr, s2);
+    };
+    if ((rc = phase1(0)) || (rc = phase2_begin(0))) { cudaDeviceSynchronize(); return rc; }
+    for (int k = 1; k < nb; ++k) {
+        // enqueue the next sub-batch's phase 1 first so the GPU stays busy while the host waits for phase 2
+        if ((rc = phase1(k)) || (rc = phase2_end(k - 1)) || (rc = phase2_begin(k))) { cudaDeviceSynchronize(); return rc; }
     }
+    rc = phase2_end(nb - 1);
+    if (rc) cudaDeviceSynchronize();
     return rc;
 }
 
@@ -981,7 +1069,7 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
     CK(cudaMemcpyAsync(d_rng, rng, sizeof(rng), cudaMemcpyHostToDevice, st));
     UnitSrc U{d_u, d_rng, nullptr, 0, 0, 0};
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
-    launch_inverse(plan, unit_ctx(c), c->d_spec, c->spec_slab, U, 1, c->d_scratch, c->d_unit_desc, O, true, st);
+    launch_inverse(plan, unit_ctx(c), c->d_spec, c->spec_slab, U, 1, c->d_scratch2, c->d_unit_desc2, O, true, st);
     c->launches += 3;
     CK(cudaMemcpyAsync(out_host, c->d_corr, sizeof(float) * no, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -997,8 +1085,9 @@ extern "C" int apd_profile(apd_ctx* c, int enable)
 {
     if (!c) return fail(APD_ERR_INVALID, "apd_profile: null context");
     CK(cudaSetDevice(c->device));
-    if (enable && !c->ev[0])
-        for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&c->ev[i]));
+    if (enable && !c->sets[0].ev[0])
+        for (auto& b : c->sets)
+            for (auto& e : b.ev) CK(cudaEventCreate(&e));
     c->profile = enable != 0;
     return APD_OK;
 }

@@ -276,7 +276,7 @@ size_t corr_inv_desc_bytes(int nunits) { return sizeof(UnitDesc) * (size_t)(nuni
 void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
                      int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st)
 {
-    static const int per_max = std::max(1, env_int2("APD_B200_PER", 8));
+    static const int per_max = std::max(1, env_int2("APD_B200_PER", 16));
     static const int keep_h = env_int2("APD_B200_KEEP_H", 1);
     static const int swap = env_int2("APD_B200_SWAP", 1);
     UnitDesc* D = static_cast<UnitDesc*>(desc);
