@@ -116,11 +116,27 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
     const long long row_off = (long long)c * kN2 + j;
     const int u_end = min(nunits, (by + 1) * per);
     const float2* cur_hs = nullptr;
-    c2 h[8];
+    c2 h[8], xn[8];
+    // software pipeline: the operands of unit u + 1 are requested right after the first exchange of unit u,
+    // so their latency is covered by two passes of arithmetic instead of by other warps
+    UnitDesc dn = load_desc(D + by * per);
+    if (dn.n_out >= 0) {
+        const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
+    }
     for (int u = by * per; u < u_end; ++u) {
-        const UnitDesc d = load_desc(D + u);
-        if (d.n_out < 0) continue;
-        const c2* __restrict__ xs = reinterpret_cast<const c2*>(d.xs + row_off);
+        const UnitDesc d = dn;
+        const bool more = u + 1 < u_end;
+        if (more) dn = load_desc(D + u + 1);
+        if (d.n_out < 0) {
+            if (more && dn.n_out >= 0) {
+                const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
+            }
+            continue;
+        }
         const c2* __restrict__ hs = reinterpret_cast<const c2*>(d.hs + row_off);
         c2 v[8];
         if (KEEP_H) {
@@ -131,14 +147,19 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
                 cur_hs = d.hs;
             }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = cmul(ldg_stream(xs + 64 * r), h[r]);
+            for (int r = 0; r < 8; ++r) v[r] = cmul(xn[r], h[r]);
         } else {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = cmul(ldg_stream(xs + 64 * r), ldg_nc(hs + 64 * r));
+            for (int r = 0; r < 8; ++r) v[r] = cmul(xn[r], ldg_nc(hs + 64 * r));
         }
         Dft2<8, +1>::run(v);
 #pragma unroll
         for (int r = 0; r < 8; ++r) sts(A.st1 ^ (8u * r), v[r]);
+        if (more && dn.n_out >= 0) {
+            const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
+        }
         group_sync<64>(q + 1);
         APD_ROW_LOAD8(A, v)
         group_sync<64>(q + 1);
@@ -208,15 +229,34 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
     const long long col_off = (long long)j * kN2 + bcol;
     const int m0 = (j % NLAST) * kN2 + bcol;                 // output index of r = 0; r adds 64 * 512
     const int u_end = min(nunits, (by + 1) * per);
+    c2 vn[8];
+    UnitDesc dn = load_desc(D + by * per);
+    if (dn.n_out >= 0) {
+        const c2* __restrict__ in = reinterpret_cast<const c2*>(W + (long long)(by * per) * M + col_off);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) vn[r] = ldg_stream(in + (long long)T1 * kN2 * r);
+    }
     for (int u = by * per; u < u_end; ++u) {
-        const UnitDesc d = load_desc(D + u);
-        if (d.n_out < 0) continue;
-        const c2* __restrict__ in = reinterpret_cast<const c2*>(W + (long long)u * M + col_off);
+        const UnitDesc d = dn;
+        const bool more = u + 1 < u_end;
+        if (more) dn = load_desc(D + u + 1);
+        const c2* __restrict__ in_next = reinterpret_cast<const c2*>(W + (long long)(u + 1) * M + col_off);
+        if (d.n_out < 0) {
+            if (more && dn.n_out >= 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) vn[r] = ldg_stream(in_next + (long long)T1 * kN2 * r);
+            }
+            continue;
+        }
         c2 v[R2 > 8 ? R2 : 8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = ldg_stream(in + (long long)T1 * kN2 * r);
+        for (int r = 0; r < 8; ++r) v[r] = vn[r];
         Dft2<8, +1>::run(v);
         col_store1<kTB>(A, v);
+        if (more && dn.n_out >= 0) {      // request the next unit's column while this one is transformed
+#pragma unroll
+            for (int r = 0; r < 8; ++r) vn[r] = ldg_stream(in_next + (long long)T1 * kN2 * r);
+        }
         __syncthreads();
         ColLoad<kTB, T1, 8>::run(A, v);
         __syncthreads();

@@ -130,12 +130,15 @@ __global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int cells_stride,
     }
 }
 
-// One thread per (chunk, group) whose section starts later than the union's: re-filter the first
-// patch_cells cells of the group's section from zero state.  patch[(ci*G + g) * patch_cells + k].
+// One warp per (chunk, group) whose section starts later than the union's: re-filter the first
+// patch_cells cells of the group's section from zero state, with the same cell-parallel scheme as
+// the main passes (zero-state run per lane, warp scan of the carries, second run for the energies).
+// patch[(ci*G + g) * patch_cells + k].
 __global__ void k_kw_patch(KwConfig K, SectionGeom Gu, const SectionGeom* __restrict__ geoms, int nsec, int G,
                            double* __restrict__ patch)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= nsec * G) return;
     const int ci = t / G, g = t % G;
     long long su, sg;
@@ -144,17 +147,37 @@ __global__ void k_kw_patch(KwConfig K, SectionGeom Gu, const SectionGeom* __rest
     section_bounds(geoms[g], ci, sg, ng);
     if (sg <= su || ng <= 0) return;                          // same start as the union: nothing to patch
     const float* __restrict__ x = geoms[g].audio + (sg - geoms[g].base);
-    double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v;
-    double* out = patch + (long long)t * K.patch_cells;
-    int pos = 0;
-    for (int k = 0; k < K.patch_cells; ++k) {
+    const int cell = K.cell;
+    double prev[4] = {0, 0, 0, 0};                            // state at the start of this group of 32 cells
+    for (int g0 = 0; g0 < K.patch_cells; g0 += 32) {
+        const int i = g0 + lane;
+        const int lo = (int)min((long long)i * cell, (long long)ng);
+        const int hi = i < K.patch_cells ? min(lo + cell, ng) : lo;
+        double s[4] = {0, 0, 0, 0}, v;
+        for (int p = lo; p < hi; ++p) kw_step(K.cf, (double)x[p], s[0], s[1], s[2], s[3], v);
+        // inclusive scan: s_i = Mc s_{i-1} + z_i  (state at the end of cell i)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            double u[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) u[r] = __shfl_up_sync(0xffffffffu, s[r], 1 << k);
+            if (lane >= (1 << k)) mat4_apply_add(K.mpow + ((1 << k) - 1) * 16, u, s);
+        }
+        mat4_apply_add(K.mpow + lane * 16, prev, s);          // + Mc^(lane+1) * prev
+        double c[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            c[r] = __shfl_up_sync(0xffffffffu, s[r], 1);
+            if (lane == 0) c[r] = prev[r];
+        }
         double e = 0;
-        const int end = min(pos + K.cell, ng);
-        for (; pos < end; ++pos) {
-            kw_step(K.cf, (double)x[pos], s1, s2, h1, h2, v);
+        for (int p = lo; p < hi; ++p) {
+            kw_step(K.cf, (double)x[p], c[0], c[1], c[2], c[3], v);
             e += v * v;
         }
-        out[k] = e;
+        if (i < K.patch_cells) patch[(long long)t * K.patch_cells + i] = e;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) prev[r] = __shfl_sync(0xffffffffu, s[r], 31);
     }
 }
 
@@ -372,7 +395,7 @@ void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom
     k_kw_cells<0><<<grid, 128, smem, st>>>(K, Gu, cells_stride, state, energy, energy_m1);
     k_kw_scan<<<(nsec * 32 + 127) / 128, 128, 0, st>>>(K, Gu, nsec, cells_stride, state);
     k_kw_cells<1><<<grid, 128, smem, st>>>(K, Gu, cells_stride, state, energy, energy_m1);
-    if (need_patch) k_kw_patch<<<(nsec * G + 63) / 64, 64, 0, st>>>(K, Gu, d_geoms, nsec, G, patch);
+    if (need_patch) k_kw_patch<<<(nsec * G * 32 + 127) / 128, 128, 0, st>>>(K, Gu, d_geoms, nsec, G, patch);
     k_kw_gate<<<(nsec * G * 32 + 127) / 128, 128, 0, st>>>(K, Gu, d_geoms, nsec, G, cells_stride, energy, energy_m1,
                                                           patch, lufs, gain);
 }
