@@ -234,6 +234,32 @@ class AudioPatternDetector:
         _lib.check(_lib.lib().apd_profile_read(self._ctx, ms, 1 if reset else 0), "apd_profile_read")
         return dict(zip(("loudness", "forward_fft", "correlate_max", "peaks_verify"), ms))
 
+    def time_correlate_stage(self, audio_dev: Any) -> tuple[float, int]:
+        """Device time (ms, CUDA events on the current stream) of the fused correlate + max stage alone over a
+        whole device-resident stream: per sub-batch the loudness and forward-FFT stages are run untimed, then
+        apd_stage_correlate_max is bracketed by events with nothing else on the GPU.  Returns (ms, launches)."""
+        torch = _torch()
+        L = _lib.lib()
+        n = audio_dev.numel()
+        C_ = self._chunk_samples
+        n_chunks = (n + C_ - 1) // C_
+        total_ms, launches = 0.0, 0
+        with torch.cuda.device(self._device):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for c0 in range(0, n_chunks, self._max_batch):
+                c1 = min(n_chunks, c0 + self._max_batch)
+                _lib.check(L.apd_stage_loudness(self._ctx, C.c_void_p(audio_dev.data_ptr()), 0, n, c0, c1, st), "stage")
+                _lib.check(L.apd_stage_forward_fft(self._ctx, st), "stage")
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = self.launch_count()
+                e0.record()
+                _lib.check(L.apd_stage_correlate_max(self._ctx, st), "stage")
+                e1.record()
+                e1.synchronize()
+                total_ms += e0.elapsed_time(e1)
+                launches += self.launch_count() - l0
+        return total_ms, launches
+
     def launch_count(self) -> int:
         return int(_lib.lib().apd_launch_count(self._ctx))
 

@@ -247,7 +247,9 @@ struct apd_ctx {
     // double-buffered (BatchSet below; the pointers above are those of the set in use).
     float2* d_scratch2 = nullptr;
     void* d_unit_desc2 = nullptr;
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr;          // phase 2
+    cudaStream_t pre = nullptr;           // loudness of the next sub-batch (latency-bound, hidden under phase 1)
+    cudaEvent_t scan_start = nullptr;
     struct BatchSet {
         float2* d_spec = nullptr;
         unsigned int* d_unit_max = nullptr;
@@ -257,12 +259,12 @@ struct apd_ctx {
         double *d_lufs = nullptr, *d_gain = nullptr;
         SectionGeom *d_geoms = nullptr, *h_geoms = nullptr;
         int chunk_begin = 0, chunk_end = 0;
-        cudaEvent_t p1_done = nullptr;
-        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t p1_done = nullptr, loud_done = nullptr;
+        cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     } sets[2];
     int cur_set = 0;
 
-    // optional stage timing (CUDA events: [0..3] on the caller's stream, [4..5] on the side stream)
+    // optional stage timing (CUDA events: [0..1] loudness stream, [2..4] caller's stream, [5..6] side stream)
     bool profile = false;
     cudaEvent_t* ev = nullptr;
     double stage_ms[4] = {0, 0, 0, 0};
@@ -351,7 +353,7 @@ static int self_correlation(apd_ctx* c, ClipHost& cl, InitTmp& t)
     const float2* hp = sb;
     CK(cudaMemcpy(t.spec_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(t.geom, &Ga, sizeof(Ga), cudaMemcpyHostToDevice));
-    UnitSrc U{nullptr, nullptr, t.ints, 1, 0, 0};                // dense: unit 0 = (section 0, clip 0)
+    UnitSrc U{nullptr, nullptr, t.ints, 1, 0, 0, 0, 0};                // dense: unit 0 = (section 0, clip 0)
     UnitCtx X{t.geom, t.ints, t.ints + 1, t.zero_ll, t.spec_ptr};
     InvOut O{t.max_bits, 1, cl.d_self_corr, (long long)(2 * L - 1), t.zero_f};
     launch_inverse(P, X, sa, P.M, U, 1, scr, t.desc, O, false, 0);
@@ -632,6 +634,11 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     c->n_slots = 256;
     c->inv_units = 512;
     if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
+    {
+        int tc = 0, tk = 0;
+        corr_inv_tiling(&tc, &tk);
+        if (tc > 0) c->inv_units = (c->inv_units + tc * tk - 1) / (tc * tk) * (tc * tk);
+    }
     c->scratch_elems = std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
     CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(c->inv_units)));
@@ -645,8 +652,17 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         CK(cudaMallocHost((void**)&b.h_counts, sizeof(int) * (S + 4)));
         CK(dalloc(&b.d_sel, (size_t)c->sel_capacity));
         CK(cudaEventCreateWithFlags(&b.p1_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b.loud_done, cudaEventDisableTiming));
     }
-    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    {
+        // both helper streams carry small latency-bound kernels: give them priority over the caller's stream so
+        // their CTAs are placed as soon as a correlate CTA retires instead of queueing behind its whole grid
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&c->pre, cudaStreamNonBlocking, hi));
+    }
+    CK(cudaEventCreateWithFlags(&c->scan_start, cudaEventDisableTiming));
     c->cur_set = 0;
     use_set(c, 0);
     c->corr_stride = (max_nout + 31) / 32 * 32;
@@ -705,10 +721,13 @@ extern "C" int apd_destroy(apd_ctx* c)
         cudaFreeHost(b.h_counts);
         cudaFreeHost(b.h_geoms);
         if (b.p1_done) cudaEventDestroy(b.p1_done);
+        if (b.loud_done) cudaEventDestroy(b.loud_done);
         for (auto& e : b.ev)
             if (e) cudaEventDestroy(e);
     }
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->pre) cudaStreamDestroy(c->pre);
+    if (c->scan_start) cudaEventDestroy(c->scan_start);
     void* ptrs[] = {c->d_scratch2, c->d_unit_desc2,
                     c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
                     c->d_win_ds, c->d_tone_P, c->d_self_max, (void*)c->d_self_corr_ptrs, (void*)c->d_win_cache_ptrs,
@@ -815,12 +834,15 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
     static const bool clip_major = !(getenv("APD_B200_CHUNK_MAJOR") && atoi(getenv("APD_B200_CHUNK_MAJOR")));
     for (auto& sc : c->shapes) {
         const int ns = (int)sc.clips.size();
-        const int nunits = B * ns;
-        for (int u0 = 0; u0 < nunits; u0 += c->inv_units) {
-            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, u0, clip_major ? B : 0};
-            launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, std::min(c->inv_units, nunits - u0),
+        int tc = 0, tk = 0;
+        if (corr_inv_supported(sc.plan) && clip_major) corr_inv_tiling(&tc, &tk);
+        // unit positions of the launch sequence (with unit tiling some positions of edge tiles are unused)
+        const long long nunits = tc > 0 ? corr_inv_dense_units(ns, B) : (long long)B * ns;
+        for (long long u0 = 0; u0 < nunits; u0 += c->inv_units) {
+            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, (int)u0, clip_major ? B : 0, tc, tk};
+            launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, (int)std::min<long long>(c->inv_units, nunits - u0),
                            c->d_scratch, c->d_unit_desc, O, false, st);
-            c->launches += 3;
+            c->launches += tc > 0 ? 2 : 3;
         }
     }
     CK(cudaGetLastError());
@@ -835,7 +857,7 @@ static void phase2_round(apd_ctx* c, int slot0, cudaStream_t st)
     const UnitCtx X = unit_ctx(c);
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
     for (int s = 0; s < S; ++s) {
-        UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0, 0};
+        UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0, 0, 0, 0};
         launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch2, c->d_unit_desc2, O, true, st);
         c->launches += 3;
     }
@@ -936,7 +958,7 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         CK(cudaStreamSynchronize(st));
     }
     phase2_tone(c, c->h_counts[S + 3], st);
-    if (c->profile) cudaEventRecord(c->ev[5], st);
+    if (c->profile) cudaEventRecord(c->ev[6], st);
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int n = c->h_counts[S + 1];
@@ -983,12 +1005,11 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
             for (int p = 0; p < c->n_clips; ++p)
                 lufs_host[(size_t)ci * c->n_clips + p] = lf[(size_t)ci * G + c->clips[p].group];
     if (c->profile) {
-        for (int i = 0; i < 3; ++i) {
+        const int pairs[4][2] = {{0, 1}, {2, 3}, {3, 4}, {5, 6}};
+        for (int i = 0; i < 4; ++i) {
             float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->stage_ms[i] += ms;
+            if (cudaEventElapsedTime(&ms, c->ev[pairs[i][0]], c->ev[pairs[i][1]]) == cudaSuccess) c->stage_ms[i] += ms;
         }
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->stage_ms[3] += ms;
     }
     return APD_OK;
 }
@@ -1005,30 +1026,37 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
     if (!c || !cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null argument");
     if (ce <= cb) return fail(APD_ERR_INVALID, "scan: empty chunk range");
     CK(cudaSetDevice(c->device));
-    cudaStream_t s2 = c->side;
+    cudaStream_t s2 = c->side, s3 = c->pre;
     *n_cand = 0;
+    // the loudness stream must see what the caller enqueued before the scan (e.g. the upload of the audio)
+    CK(cudaEventRecord(c->scan_start, s1));
+    CK(cudaStreamWaitEvent(s3, c->scan_start, 0));
     const int nb = (ce - cb + c->maxB - 1) / c->maxB;
     const bool prof = c->profile;
     int rc = APD_OK;
     auto phase1 = [&](int k) -> int {
         use_set(c, k & 1);
         const int b0 = cb + k * c->maxB, b1 = std::min<int>(ce, b0 + c->maxB);
-        int r = stage_begin(c, audio, base, n, b0, b1, s1);
+        // loudness on its own stream: enqueued while the previous sub-batch's correlate stage is still running
+        int r = stage_begin(c, audio, base, n, b0, b1, s3);
         if (r) return r;
-        if (prof) cudaEventRecord(c->ev[0], s1);
-        if ((r = stage_loudness(c, s1))) return r;
-        if (prof) cudaEventRecord(c->ev[1], s1);
-        if ((r = stage_forward(c, s1))) return r;
+        if (prof) cudaEventRecord(c->ev[0], s3);
+        if ((r = stage_loudness(c, s3))) return r;
+        if (prof) cudaEventRecord(c->ev[1], s3);
+        CK(cudaEventRecord(c->sets[k & 1].loud_done, s3));
+        CK(cudaStreamWaitEvent(s1, c->sets[k & 1].loud_done, 0));
         if (prof) cudaEventRecord(c->ev[2], s1);
-        if ((r = stage_correlate_max(c, s1))) return r;
+        if ((r = stage_forward(c, s1))) return r;
         if (prof) cudaEventRecord(c->ev[3], s1);
+        if ((r = stage_correlate_max(c, s1))) return r;
+        if (prof) cudaEventRecord(c->ev[4], s1);
         CK(cudaEventRecord(c->sets[k & 1].p1_done, s1));
         return APD_OK;
     };
     auto phase2_begin = [&](int k) -> int {
         use_set(c, k & 1);
         CK(cudaStreamWaitEvent(s2, c->sets[k & 1].p1_done, 0));
-        if (prof) cudaEventRecord(c->ev[4], s2);
+        if (prof) cudaEventRecord(c->ev[5], s2);
         return stage_peaks_verify(c, s2);
     };
     auto phase2_end = [&](int k) -> int {
@@ -1067,7 +1095,7 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
     CK(dalloc(&d_rng, 2));
     CK(cudaMemcpyAsync(d_u, &u, sizeof(u), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_rng, rng, sizeof(rng), cudaMemcpyHostToDevice, st));
-    UnitSrc U{d_u, d_rng, nullptr, 0, 0, 0};
+    UnitSrc U{d_u, d_rng, nullptr, 0, 0, 0, 0, 0};
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
     launch_inverse(plan, unit_ctx(c), c->d_spec, c->spec_slab, U, 1, c->d_scratch2, c->d_unit_desc2, O, true, st);
     c->launches += 3;

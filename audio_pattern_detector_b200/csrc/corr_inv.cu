@@ -55,6 +55,12 @@ __global__ void k_unit_desc(UnitSrc U, UnitCtx C, const float2* __restrict__ spe
     D[u] = d;
 }
 
+__device__ __forceinline__ c2 ldg_l2(const c2* p)          // L2 only: W may have been written by another SM of this launch
+{
+    c2 r;
+    asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(r.v) : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ UnitDesc load_desc(const UnitDesc* p)
 {
     UnitDesc d;
@@ -97,14 +103,14 @@ template <int R> __device__ __forceinline__ c2 row_ld(const RowAddr<8>& A)
     v[0] = row_ld<0>(A); v[1] = row_ld<1>(A); v[2] = row_ld<2>(A); v[3] = row_ld<3>(A);          \
     v[4] = row_ld<4>(A); v[5] = row_ld<5>(A); v[6] = row_ld<6>(A); v[7] = row_ld<7>(A);
 
-template <bool KEEP_H>
-__global__ void __launch_bounds__(kRowsPerCta * 64, KEEP_H ? 2 : 3)
-k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+// One work item of the row pass: rows [tile * ROWS, (tile + 1) * ROWS) of units [u_begin, u_end); unit u writes
+// its rows to Wg + (u - u_begin) * M.  buf: ROWS * 512 complex of shared memory, 1 KB aligned.
+template <int ROWS, bool KEEP_H>
+__device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ D, int u_begin, int u_end, int tile,
+                                          int M, float2* __restrict__ Wg)
 {
-    __shared__ __align__(1024) c2 buf[kRowsPerCta * kN2];
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
-    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
-    const int c = bx * kRowsPerCta + q;
+    const int c = tile * ROWS + q;
     const RowAddr<8> A(smem_addr(buf + q * kN2), j);
     float2 tw2[8], tw3[8], fs[8];
     pass_twiddles<8, +1, 8>(j, tw2);
@@ -114,18 +120,17 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
         geometric<8>(twiddle_frac(j * c, invM, +1.0f), twiddle_frac(64 * c, invM, +1.0f), fs);
     }
     const long long row_off = (long long)c * kN2 + j;
-    const int u_end = min(nunits, (by + 1) * per);
     const float2* cur_hs = nullptr;
     c2 h[8], xn[8];
     // software pipeline: the operands of unit u + 1 are requested right after the first exchange of unit u,
     // so their latency is covered by two passes of arithmetic instead of by other warps
-    UnitDesc dn = load_desc(D + by * per);
+    UnitDesc dn = load_desc(D + u_begin);
     if (dn.n_out >= 0) {
         const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
 #pragma unroll
         for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
     }
-    for (int u = by * per; u < u_end; ++u) {
+    for (int u = u_begin; u < u_end; ++u) {
         const UnitDesc d = dn;
         const bool more = u + 1 < u_end;
         if (more) dn = load_desc(D + u + 1);
@@ -172,10 +177,19 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
         group_sync<64>(q + 1);
         bfly_tw<8>(v, tw3);
         Dft2<8, +1>::run(v);
-        c2* __restrict__ out = reinterpret_cast<c2*>(W + (long long)u * M + row_off);
+        c2* __restrict__ out = reinterpret_cast<c2*>(Wg + (long long)(u - u_begin) * M + row_off);
 #pragma unroll
         for (int r = 0; r < 8; ++r) out[64 * r] = cmul(v[r], fs[r]);
     }
+}
+
+template <bool KEEP_H>
+__global__ void __launch_bounds__(kRowsPerCta * 64, KEEP_H ? 2 : 3)
+k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+{
+    __shared__ __align__(1024) c2 buf[kRowsPerCta * kN2];
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    rows_item<kRowsPerCta, KEEP_H>(buf, D, by * per, min(nunits, (by + 1) * per), bx, M, W + (long long)(by * per) * M);
 }
 
 // ---------------------------------------------------------------- columns
@@ -196,21 +210,22 @@ __device__ __forceinline__ float2 post_const10(int r)
     return make_float2(c[r], s[r]);
 }
 
+// One work item of the column pass: columns [tile * kTB, (tile + 1) * kTB) of units [u_begin, u_end); unit u reads
+// Wg + (u - u_begin) * M and (WRITE) writes corr_g + (u - u_begin) * corr_stride.
+// raw: N1 * kTB + ColLayout<kTB>::SLACK complex of shared memory, 1 KB aligned; red: one float per warp.
 template <class S, bool WRITE>
-__global__ void __launch_bounds__(kTB * (S::N / 8), S::N == 512 ? 3 : 2)
-k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
-            unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride, int swap)
+__device__ __forceinline__ void cols_item(c2* raw, float* red, const UnitDesc* __restrict__ D, int u_begin, int u_end,
+                                          int tile, int M, const float2* __restrict__ Wg,
+                                          unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr_g,
+                                          long long corr_stride)
 {
     constexpr int N1 = S::N;
     constexpr int T1 = N1 / 8;            // butterflies per column in the radix-8 passes
     constexpr int R2 = S::R2;             // last radix: 8 or 10
     constexpr int NLAST = N1 / R2;        // 64 butterflies in the last pass
     constexpr int NW = kTB * T1 / 32;     // warps per CTA
-    __shared__ __align__(1024) c2 raw[N1 * kTB + ColLayout<kTB>::SLACK];
-    __shared__ float red[NW];
     const int q = threadIdx.x % kTB, j = threadIdx.x / kTB;
-    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
-    const int bcol = bx * kTB + q;
+    const int bcol = tile * kTB + q;
     const ColAddr<kTB> A(raw, j, q);
     float2 tw2[8], tw3[R2];
     pass_twiddles<8, +1, 8>(j, tw2);
@@ -228,23 +243,22 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
     }
     const long long col_off = (long long)j * kN2 + bcol;
     const int m0 = (j % NLAST) * kN2 + bcol;                 // output index of r = 0; r adds 64 * 512
-    const int u_end = min(nunits, (by + 1) * per);
     c2 vn[8];
-    UnitDesc dn = load_desc(D + by * per);
+    UnitDesc dn = load_desc(D + u_begin);
     if (dn.n_out >= 0) {
-        const c2* __restrict__ in = reinterpret_cast<const c2*>(W + (long long)(by * per) * M + col_off);
+        const c2* __restrict__ in = reinterpret_cast<const c2*>(Wg + col_off);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) vn[r] = ldg_stream(in + (long long)T1 * kN2 * r);
+        for (int r = 0; r < 8; ++r) vn[r] = ldg_l2(in + (long long)T1 * kN2 * r);
     }
-    for (int u = by * per; u < u_end; ++u) {
+    for (int u = u_begin; u < u_end; ++u) {
         const UnitDesc d = dn;
         const bool more = u + 1 < u_end;
         if (more) dn = load_desc(D + u + 1);
-        const c2* __restrict__ in_next = reinterpret_cast<const c2*>(W + (long long)(u + 1) * M + col_off);
+        const c2* __restrict__ in_next = reinterpret_cast<const c2*>(Wg + (long long)(u + 1 - u_begin) * M + col_off);
         if (d.n_out < 0) {
             if (more && dn.n_out >= 0) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) vn[r] = ldg_stream(in_next + (long long)T1 * kN2 * r);
+                for (int r = 0; r < 8; ++r) vn[r] = ldg_l2(in_next + (long long)T1 * kN2 * r);
             }
             continue;
         }
@@ -255,7 +269,7 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
         col_store1<kTB>(A, v);
         if (more && dn.n_out >= 0) {      // request the next unit's column while this one is transformed
 #pragma unroll
-            for (int r = 0; r < 8; ++r) vn[r] = ldg_stream(in_next + (long long)T1 * kN2 * r);
+            for (int r = 0; r < 8; ++r) vn[r] = ldg_l2(in_next + (long long)T1 * kN2 * r);
         }
         __syncthreads();
         ColLoad<kTB, T1, 8>::run(A, v);
@@ -270,7 +284,7 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
 #pragma unroll
             for (int r = 0; r < R2; ++r) v[r] = cmul(v[r], tw3[r]);
             Dft2<R2, +1>::run(v);
-            float* __restrict__ out = WRITE ? corr + (long long)u * corr_stride : nullptr;
+            float* __restrict__ out = WRITE ? corr_g + (long long)(u - u_begin) * corr_stride : nullptr;
             const int lim0 = d.n_out - m0, lim1 = d.n_out - M - m0;      // valid iff 32768 r < lim
 #pragma unroll
             for (int r = 0; r < R2; ++r) {
@@ -302,6 +316,89 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
     }
 }
 
+template <class S, bool WRITE>
+__global__ void __launch_bounds__(kTB * (S::N / 8), S::N == 512 ? 3 : 2)
+k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
+            unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride, int swap)
+{
+    __shared__ __align__(1024) c2 raw[S::N * kTB + ColLayout<kTB>::SLACK];
+    __shared__ float red[kTB * (S::N / 8) / 32];
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int u0 = by * per;
+    cols_item<S, WRITE>(raw, red, D, u0, min(nunits, u0 + per), bx, M, W + (long long)u0 * M, unit_max_bits,
+                        WRITE ? corr + (long long)u0 * corr_stride : nullptr, corr_stride);
+}
+
+// ---------------------------------------------------------------- fused persistent kernel
+// Phase 1 (max only) as ONE persistent launch in which the four-step intermediate W never leaves L2.
+// Units are taken in groups of U; a group's row pass (128 items: 4 or 5 rows each) and column pass (128 items: 4
+// columns each) are work items of one queue, ordered
+//     rows(0) .. rows(LAG-1), [rows(s), cols(s-LAG)] for s = LAG .. G-1, cols(G-LAG) .. cols(G-1)
+// and handed out by an atomic counter.  A column item waits until all 128 row items of its group have
+// published their W (release/acquire on a per-group counter); W lives in `slots` group-sized slots that are
+// recycled once the group that used a slot has been read (second counter).  Every item waits only for items
+// that were handed out before it, so the schedule cannot deadlock whatever the number of resident CTAs; with
+// U * (LAG + 2) units in flight (~50 MB) W is written to and read back from the 126 MB L2, not HBM.
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <class S, bool KEEP_H>
+__global__ void __launch_bounds__(S::N / 2, 2)
+k_corr_fused(const UnitDesc* __restrict__ D, int nunits, int U, int lag, int slots, int M, float2* __restrict__ W,
+             unsigned int* __restrict__ unit_max_bits, int* __restrict__ counters)
+{
+    constexpr int N1 = S::N;
+    constexpr int ROWS = N1 / 128;                       // rows per row item; ROWS * 64 == kTB * N1 / 8 threads
+    constexpr int ITEMS = 128;                           // row items == column items per group
+    constexpr int SMEM = (ROWS * kN2 > N1 * kTB + ColLayout<kTB>::SLACK) ? ROWS * kN2 : N1 * kTB + ColLayout<kTB>::SLACK;
+    static_assert(kN2 / kTB == ITEMS && N1 / ROWS == ITEMS, "work item counts");
+    __shared__ __align__(1024) c2 smem[SMEM];
+    __shared__ float red[N1 / 2 / 32];
+    __shared__ int s_item;
+    const int G = (nunits + U - 1) / U;
+    if (lag > G) lag = G;
+    const int total = 2 * G * ITEMS;
+    int* rows_done = counters + 1;
+    int* cols_done = counters + 1 + G;
+    for (;;) {
+        __syncthreads();                                 // previous item done with smem and s_item
+        if (threadIdx.x == 0) s_item = atomicAdd(counters, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int p = item / ITEMS, tile = item % ITEMS;
+        bool is_rows;
+        int g;
+        if (p < lag) { is_rows = true; g = p; }
+        else if (p < 2 * G - lag) { const int t = p - lag; is_rows = !(t & 1); g = is_rows ? lag + (t >> 1) : (t >> 1); }
+        else { is_rows = false; g = p - G; }
+        const int u0 = g * U, u1 = min(nunits, u0 + U);
+        float2* Wg = W + (long long)((g % slots) * U) * M;
+        if (is_rows) {
+            if (g >= slots) {                            // the slot's previous tenant must have been read
+                if (threadIdx.x == 0)
+                    while (ld_acquire(cols_done + g - slots) < ITEMS) __nanosleep(100);
+                __syncthreads();
+            }
+            rows_item<ROWS, KEEP_H>(smem, D, u0, u1, tile, M, Wg);
+            __threadfence();                             // publish this thread's W stores
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(rows_done + g, 1);
+        } else {
+            if (threadIdx.x == 0)
+                while (ld_acquire(rows_done + g) < ITEMS) __nanosleep(100);
+            __syncthreads();
+            cols_item<S, false>(smem, red, D, u0, u1, tile, M, Wg, unit_max_bits, nullptr, 0);
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(cols_done + g, 1);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- launcher
 static int env_int2(const char* name, int dflt)
 {
@@ -311,7 +408,27 @@ static int env_int2(const char* name, int dflt)
 
 bool corr_inv_supported(const Fft4Plan& P) { return P.N2 == kN2 && (P.N1 == 512 || P.N1 == 640); }
 
-size_t corr_inv_desc_bytes(int nunits) { return sizeof(UnitDesc) * (size_t)(nunits > 0 ? nunits : 1); }
+// descriptors, then the fused kernel's counters: queue head + two per group (at most one group per unit)
+static size_t desc_counters_offset(int nunits) { return sizeof(UnitDesc) * (size_t)(nunits > 0 ? nunits : 1); }
+size_t corr_inv_desc_bytes(int nunits) { return desc_counters_offset(nunits) + sizeof(int) * (size_t)(2 * nunits + 8); }
+
+static int fused_tc() { static int v = env_int2("APD_B200_FUSED_TC", 4); return v; }     // clips per unit tile
+static int fused_tk() { static int v = env_int2("APD_B200_FUSED_TK", 2); return v; }     // chunks per unit tile
+// off by default: measured slower than the two-kernel path ("fused persistent variant")
+static int fused_on() { static int v = env_int2("APD_B200_FUSED", 0) && fused_tc() > 0 && fused_tk() > 0; return v; }
+
+void corr_inv_tiling(int* tile_clips, int* tile_chunks)
+{
+    *tile_clips = fused_on() ? fused_tc() : 0;
+    *tile_chunks = fused_on() ? fused_tk() : 0;
+}
+
+long long corr_inv_dense_units(int ns, int nb)
+{
+    if (!fused_on()) return (long long)ns * nb;
+    const int tc = fused_tc(), tk = fused_tk();
+    return (long long)((ns + tc - 1) / tc) * ((nb + tk - 1) / tk) * tc * tk;
+}
 
 void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
                      int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st)
@@ -319,8 +436,34 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
     static const int per_max = std::max(1, env_int2("APD_B200_PER", 16));
     static const int keep_h = env_int2("APD_B200_KEEP_H", 1);
     static const int swap = env_int2("APD_B200_SWAP", 1);
+    static const int lag = std::max(1, env_int2("APD_B200_FUSED_LAG", 1));
+    static const int slots = std::max(lag + 1, env_int2("APD_B200_FUSED_SLOTS", 4));
     UnitDesc* D = static_cast<UnitDesc*>(desc);
     k_unit_desc<<<(nunits + 127) / 128, 128, 0, st>>>(U, C, spec, spec_slab, out, nunits, write ? 1 : 0, D);
+    if (!write && U.tc > 0) {
+        // fused persistent launch: one group = one unit tile
+        const int gu = U.tc * U.tk;
+        int* counters = reinterpret_cast<int*>(static_cast<char*>(desc) + desc_counters_offset(nunits));
+        cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)(2 * ((nunits + gu - 1) / gu) + 1), st);
+        static int grid512 = 0, grid640 = 0;
+        if (!grid512) {
+            int dev = 0, sms = 148, b = 2;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_corr_fused<Shape512, true>, 256, 0);
+            grid512 = sms * std::max(b, 1);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_corr_fused<Shape640, true>, 320, 0);
+            grid640 = sms * std::max(b, 1);
+        }
+        if (P.N1 == 512) {
+            if (keep_h) k_corr_fused<Shape512, true><<<grid512, 256, 0, st>>>(D, nunits, gu, lag, slots, P.M, scratch, out.unit_max_bits, counters);
+            else k_corr_fused<Shape512, false><<<grid512, 256, 0, st>>>(D, nunits, gu, lag, slots, P.M, scratch, out.unit_max_bits, counters);
+        } else {
+            if (keep_h) k_corr_fused<Shape640, true><<<grid640, 320, 0, st>>>(D, nunits, gu, lag, slots, P.M, scratch, out.unit_max_bits, counters);
+            else k_corr_fused<Shape640, false><<<grid640, 320, 0, st>>>(D, nunits, gu, lag, slots, P.M, scratch, out.unit_max_bits, counters);
+        }
+        return;
+    }
     // keep at least ~8 CTAs per SM in the grid; otherwise amortise the twiddles over up to `per` units
     int per = per_max;
     while (per > 1 && (long long)((nunits + per - 1) / per) * 64 < 148 * 8) per >>= 1;

@@ -51,6 +51,9 @@ struct UnitSrc {
     int ns;                  //        a clip, so its spectrum rows stay in L1/L2 across the per-CTA unit loop)
     int u0;                  // first unit of this launch (offset into list / dense numbering)
     int nb;                  // dense: chunks in the batch
+    int tc, tk;              // dense, tiled (tc > 0): units come in tiles of tc clips x tk chunks (clip-major inside a
+                             // tile, chunk tiles fastest), so a group of tc*tk consecutive units shares tk section
+                             // spectra and tc clip spectra; positions beyond the clip / chunk range are unused
 };
 
 // Returns false if launch-local unit u is not this launch's to process.
@@ -60,6 +63,15 @@ __device__ __forceinline__ bool get_unit(const UnitSrc& s, int u, int2* unit)
     if (s.list) {
         if (u < s.list_begin[0] || u >= s.list_begin[1]) return false;
         *unit = s.list[u];
+        return true;
+    }
+    if (s.tc > 0) {
+        const int per_tile = s.tc * s.tk, ktiles = (s.nb + s.tk - 1) / s.tk;
+        const int t = u / per_tile, i = u - t * per_tile;
+        const int ct = t / ktiles, kt = t - ct * ktiles;
+        const int ci = kt * s.tk + i % s.tk, k = ct * s.tc + i / s.tk;
+        if (ci >= s.nb || k >= s.ns) return false;
+        *unit = make_int2(ci, s.shape_clips[k]);
         return true;
     }
     *unit = s.nb > 0 ? make_int2(u % s.nb, s.shape_clips[u / s.nb]) : make_int2(u / s.ns, s.shape_clips[u % s.ns]);
@@ -112,6 +124,10 @@ void launch_inverse(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lon
 // corr_inv.cu: the register-resident packed-arithmetic kernels for M = N1 x 512, N1 in {512, 640}
 bool corr_inv_supported(const Fft4Plan& P);
 size_t corr_inv_desc_bytes(int nunits);
+// Phase-1 unit tiling of the fused persistent kernel (0 x 0: fused kernel disabled) and the number of unit
+// positions a dense launch sequence has to cover for ns clips x nb chunks.
+void corr_inv_tiling(int* tile_clips, int* tile_chunks);
+long long corr_inv_dense_units(int ns, int nb);
 void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
                      int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st);
 
