@@ -94,24 +94,26 @@ struct RowAddr {
     }
 };
 
-template <int R> __device__ __forceinline__ c2 row_ld(const RowAddr<8>& A)
+template <int R, unsigned OFF> __device__ __forceinline__ c2 row_ld(const RowAddr<8>& A)
 {
-    return (R & 1) ? lds<512 * R>(A.ld1) : lds<512 * R>(A.ld0);
+    return (R & 1) ? lds<OFF + 512 * R>(A.ld1) : lds<OFF + 512 * R>(A.ld0);
 }
 
-#define APD_ROW_LOAD8(A, v)                                                                       \
-    v[0] = row_ld<0>(A); v[1] = row_ld<1>(A); v[2] = row_ld<2>(A); v[3] = row_ld<3>(A);          \
-    v[4] = row_ld<4>(A); v[5] = row_ld<5>(A); v[6] = row_ld<6>(A); v[7] = row_ld<7>(A);
+#define APD_ROW_LOAD8(A, OFF, v)                                                                              \
+    v[0] = row_ld<0, OFF>(A); v[1] = row_ld<1, OFF>(A); v[2] = row_ld<2, OFF>(A); v[3] = row_ld<3, OFF>(A);  \
+    v[4] = row_ld<4, OFF>(A); v[5] = row_ld<5, OFF>(A); v[6] = row_ld<6, OFF>(A); v[7] = row_ld<7, OFF>(A);
 
 // One work item of the row pass: rows [tile * ROWS, (tile + 1) * ROWS) of units [u_begin, u_end); unit u writes
-// its rows to Wg + (u - u_begin) * M.  buf: ROWS * 512 complex of shared memory, 1 KB aligned.
+// its rows to Wg + (u - u_begin) * M.  buf: ROWS * 2 * 512 complex of shared memory, 1 KB aligned.
 template <int ROWS, bool KEEP_H>
 __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ D, int u_begin, int u_end, int tile,
                                           int M, float2* __restrict__ Wg)
 {
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
     const int c = tile * ROWS + q;
-    const RowAddr<8> A(smem_addr(buf + q * kN2), j);
+    // two exchange buffers per row (pass 1 -> 2 and pass 2 -> 3): one barrier per exchange, none for reuse
+    const RowAddr<8> A(smem_addr(buf + q * (2 * kN2)), j);
+    constexpr unsigned kB = kN2 * 8u;                      // byte offset of the second buffer
     float2 tw2[8], tw3[8], fs[8];
     pass_twiddles<8, +1, 8>(j, tw2);
     pass_twiddles<8, +1, 64>(j, tw3);
@@ -166,15 +168,13 @@ __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ 
             for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
         }
         group_sync<64>(q + 1);
-        APD_ROW_LOAD8(A, v)
-        group_sync<64>(q + 1);
+        APD_ROW_LOAD8(A, 0, v)
         bfly_tw<8>(v, tw2);
         Dft2<8, +1>::run(v);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) sts(A.st2 ^ (72u * r), v[r]);
+        for (int r = 0; r < 8; ++r) sts((A.st2 + kB) ^ (72u * r), v[r]);
         group_sync<64>(q + 1);
-        APD_ROW_LOAD8(A, v)
-        group_sync<64>(q + 1);
+        APD_ROW_LOAD8(A, kB, v)
         bfly_tw<8>(v, tw3);
         Dft2<8, +1>::run(v);
         c2* __restrict__ out = reinterpret_cast<c2*>(Wg + (long long)(u - u_begin) * M + row_off);
@@ -187,7 +187,7 @@ template <bool KEEP_H>
 __global__ void __launch_bounds__(kRowsPerCta * 64, KEEP_H ? 2 : 3)
 k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
 {
-    __shared__ __align__(1024) c2 buf[kRowsPerCta * kN2];
+    __shared__ __align__(1024) c2 buf[kRowsPerCta * 2 * kN2];
     const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
     rows_item<kRowsPerCta, KEEP_H>(buf, D, by * per, min(nunits, (by + 1) * per), bx, M, W + (long long)(by * per) * M);
 }
@@ -212,7 +212,7 @@ __device__ __forceinline__ float2 post_const10(int r)
 
 // One work item of the column pass: columns [tile * kTB, (tile + 1) * kTB) of units [u_begin, u_end); unit u reads
 // Wg + (u - u_begin) * M and (WRITE) writes corr_g + (u - u_begin) * corr_stride.
-// raw: N1 * kTB + ColLayout<kTB>::SLACK complex of shared memory, 1 KB aligned; red: one float per warp.
+// raw: 2 * N1 * kTB + ColLayout<kTB>::SLACK complex of shared memory, 1 KB aligned; red: two floats per warp.
 template <class S, bool WRITE>
 __device__ __forceinline__ void cols_item(c2* raw, float* red, const UnitDesc* __restrict__ D, int u_begin, int u_end,
                                           int tile, int M, const float2* __restrict__ Wg,
@@ -243,6 +243,8 @@ __device__ __forceinline__ void cols_item(c2* raw, float* red, const UnitDesc* _
     }
     const long long col_off = (long long)j * kN2 + bcol;
     const int m0 = (j % NLAST) * kN2 + bcol;                 // output index of r = 0; r adds 64 * 512
+    constexpr unsigned kBufB = N1 * kTB * 8u;                // second exchange buffer (pass 2 -> 3)
+    int pending = -1, parity = 0;                            // unit whose per-warp maxima wait in red[parity ^ 1]
     c2 vn[8];
     UnitDesc dn = load_desc(D + u_begin);
     if (dn.n_out >= 0) {
@@ -272,15 +274,19 @@ __device__ __forceinline__ void cols_item(c2* raw, float* red, const UnitDesc* _
             for (int r = 0; r < 8; ++r) vn[r] = ldg_l2(in_next + (long long)T1 * kN2 * r);
         }
         __syncthreads();
+        if (!WRITE && pending >= 0 && threadIdx.x < 32) {     // block maximum of the previous unit (see below)
+            float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
+        }
         ColLoad<kTB, T1, 8>::run(A, v);
-        __syncthreads();
         bfly_tw<8>(v, tw2);
         Dft2<8, +1>::run(v);
-        col_store2<kTB>(A, v);
+        col_store2<kTB, kBufB>(A, v);
         __syncthreads();
         float best = 0.0f;
         if (N1 == 512 || j < NLAST) {
-            ColLoad<kTB, 64, R2>::run(A, v);
+            ColLoad<kTB, 64, R2, kBufB>::run(A, v);
 #pragma unroll
             for (int r = 0; r < R2; ++r) v[r] = cmul(v[r], tw3[r]);
             Dft2<R2, +1>::run(v);
@@ -304,14 +310,20 @@ __device__ __forceinline__ void cols_item(c2* raw, float* red, const UnitDesc* _
             }
         }
         if (!WRITE) {
+            // per-warp maxima go to red[parity]; they are combined after the NEXT barrier the CTA passes anyway
+            // (the first exchange of the next unit, or the one after the loop), so a unit costs two barriers
             best = warp_max(best);
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+            if ((threadIdx.x & 31) == 0) red[parity * NW + (threadIdx.x >> 5)] = best;
+            pending = d.max_idx;
+            parity ^= 1;
         }
-        __syncthreads();                  // exchange buffer free for the next unit; red[] complete
-        if (!WRITE && threadIdx.x < 32) {
-            float t = threadIdx.x < NW ? red[threadIdx.x] : 0.0f;
+    }
+    if (!WRITE) {
+        __syncthreads();
+        if (pending >= 0 && threadIdx.x < 32) {
+            float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
             t = warp_max(t);
-            if (threadIdx.x == 0) atomicMax(unit_max_bits + d.max_idx, __float_as_uint(t));
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
         }
     }
 }
@@ -321,8 +333,8 @@ __global__ void __launch_bounds__(kTB * (S::N / 8), S::N == 512 ? 3 : 2)
 k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
             unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride, int swap)
 {
-    __shared__ __align__(1024) c2 raw[S::N * kTB + ColLayout<kTB>::SLACK];
-    __shared__ float red[kTB * (S::N / 8) / 32];
+    __shared__ __align__(1024) c2 raw[2 * S::N * kTB + ColLayout<kTB>::SLACK];
+    __shared__ float red[2 * (kTB * (S::N / 8) / 32)];
     const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
     const int u0 = by * per;
     cols_item<S, WRITE>(raw, red, D, u0, min(nunits, u0 + per), bx, M, W + (long long)u0 * M, unit_max_bits,
@@ -354,10 +366,10 @@ k_corr_fused(const UnitDesc* __restrict__ D, int nunits, int U, int lag, int slo
     constexpr int N1 = S::N;
     constexpr int ROWS = N1 / 128;                       // rows per row item; ROWS * 64 == kTB * N1 / 8 threads
     constexpr int ITEMS = 128;                           // row items == column items per group
-    constexpr int SMEM = (ROWS * kN2 > N1 * kTB + ColLayout<kTB>::SLACK) ? ROWS * kN2 : N1 * kTB + ColLayout<kTB>::SLACK;
+    constexpr int SMEM = (2 * ROWS * kN2 > 2 * N1 * kTB + ColLayout<kTB>::SLACK) ? 2 * ROWS * kN2 : 2 * N1 * kTB + ColLayout<kTB>::SLACK;
     static_assert(kN2 / kTB == ITEMS && N1 / ROWS == ITEMS, "work item counts");
     __shared__ __align__(1024) c2 smem[SMEM];
-    __shared__ float red[N1 / 2 / 32];
+    __shared__ float red[2 * (N1 / 2 / 32)];
     __shared__ int s_item;
     const int G = (nunits + U - 1) / U;
     if (lag > G) lag = G;

@@ -230,12 +230,14 @@ struct ColAddr {
 };
 
 // v[r] = exchange[j + T r], r < R
-template <int TB, int T, int R> struct ColLoad {
+// OFF: byte offset of the exchange buffer used (a multiple of ColLayout<TB>::ALIGN) when a kernel ping-pongs
+// between two buffers to save the barrier that protects buffer reuse.
+template <int TB, int T, int R, int OFF = 0> struct ColLoad {
     template <int r> static __device__ __forceinline__ c2 one(const ColAddr<TB>& A)
     {
         // ((j >> 3) + (T / 8) r) & SW differs from (j >> 3) & SW only for T = 80, SW = 3, odd r
         constexpr bool alt = (T == 80) && (ColLayout<TB>::SW == 3) && (r & 1);
-        return lds<8 * TB * T * r>(alt ? A.ld_b : A.ld_a);
+        return lds<OFF + 8 * TB * T * r>(alt ? A.ld_b : A.ld_a);
     }
     static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* v)
     {
@@ -244,15 +246,17 @@ template <int TB, int T, int R> struct ColLoad {
         if (R == 10) { v[8] = one<8>(A); v[9] = one<9>(A); }
     }
 };
-template <int TB> __device__ __forceinline__ void col_store1(const ColAddr<TB>& A, const c2* v)
+template <int TB, unsigned OFF = 0> __device__ __forceinline__ void col_store1(const ColAddr<TB>& A, const c2* v)
 {
+    static_assert(OFF % ColLayout<TB>::ALIGN == 0, "buffer offset must keep the store address alignment");
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sts(A.st1 ^ (8u * TB * r), v[r]);
+    for (int r = 0; r < 8; ++r) sts((A.st1 + OFF) ^ (8u * TB * r), v[r]);
 }
-template <int TB> __device__ __forceinline__ void col_store2(const ColAddr<TB>& A, const c2* v)
+template <int TB, unsigned OFF = 0> __device__ __forceinline__ void col_store2(const ColAddr<TB>& A, const c2* v)
 {
+    static_assert(OFF % ColLayout<TB>::ALIGN == 0, "buffer offset must keep the store address alignment");
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sts(A.st2 ^ (8u * TB * (8 * r + (r & ColLayout<TB>::SW))), v[r]);
+    for (int r = 0; r < 8; ++r) sts((A.st2 + OFF) ^ (8u * TB * (8 * r + (r & ColLayout<TB>::SW))), v[r]);
 }
 
 }  // namespace apd
