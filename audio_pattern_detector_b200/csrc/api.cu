@@ -659,6 +659,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         // their CTAs are placed as soon as a correlate CTA retires instead of queueing behind its whole grid
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        if (const char* e = getenv("APD_B200_PRIO")) if (!atoi(e)) hi = lo;
         CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&c->pre, cudaStreamNonBlocking, hi));
     }
@@ -1026,7 +1027,8 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
     if (!c || !cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null argument");
     if (ce <= cb) return fail(APD_ERR_INVALID, "scan: empty chunk range");
     CK(cudaSetDevice(c->device));
-    cudaStream_t s2 = c->side, s3 = c->pre;
+    static const bool loud_stream = !(getenv("APD_B200_LOUD_STREAM") && !atoi(getenv("APD_B200_LOUD_STREAM")));
+    cudaStream_t s2 = c->side, s3 = loud_stream ? c->pre : s1;
     *n_cand = 0;
     // the loudness stream must see what the caller enqueued before the scan (e.g. the upload of the audio)
     CK(cudaEventRecord(c->scan_start, s1));

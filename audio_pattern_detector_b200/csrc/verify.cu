@@ -652,7 +652,7 @@ k_emit(VerifyArgs A, int nslots)
 void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
 {
     if (nslots <= 0) return;
-    dim3 gn(8, nslots);
+    dim3 gn(32, nslots);      // x: peaks of a unit in parallel (short clips can keep dozens); idle CTAs exit at once
     k_verify_normal<<<gn, 256, 0, st>>>(A);
     ++*launches;
 }
