@@ -70,13 +70,49 @@ class Candidate:
     timestamp: float
 
 
-@dataclass
+# memory image of apd_candidate (include/apd_b200.h), 176 bytes
+CAND_DTYPE = np.dtype([("chunk", "<i4"), ("clip", "<i4"), ("peak", "<i4"), ("flags", "<i4"), ("height", "<f4"),
+                       ("similarity_whole", "<f4"), ("similarity_middle", "<f4"), ("reserved", "<f4"),
+                       ("pearson", "<f8", (3,)), ("tone", "<f8", (3, 5))])
+assert CAND_DTYPE.itemsize == C.sizeof(_lib.Candidate)
+
+
 class ScanResult:
-    peak_times: dict[str, list[float]]
-    events: list[tuple[float, str]]           # callback order
-    candidates: list[Candidate]
-    unit_trace: Optional[dict[tuple[int, str], dict[str, Any]]]
-    total_time: float
+    """Detections of a scan.  ``records`` is the raw candidate table (CAND_DTYPE, ordered by chunk, clip,
+    peak) with a parallel ``timestamps`` array; ``candidates`` materialises :class:`Candidate` objects on
+    first use (the hot path never does)."""
+
+    def __init__(self, peak_times: dict[str, list[float]], events: list[tuple[float, str]],
+                 records: "NDArray[Any]", timestamps: "NDArray[np.float64]", clip_names: list[str],
+                 unit_trace: Optional[dict[tuple[int, str], dict[str, Any]]], total_time: float) -> None:
+        self.peak_times = peak_times
+        self.events = events                      # callback order
+        self.records = records
+        self.timestamps = timestamps
+        self.unit_trace = unit_trace
+        self.total_time = total_time
+        self._clip_names = clip_names
+        self._candidates: Optional[list[Candidate]] = None
+
+    @property
+    def n_candidates(self) -> int:
+        return int(self.records.shape[0])
+
+    @property
+    def candidates(self) -> list[Candidate]:
+        if self._candidates is None:
+            out = []
+            for r, t in zip(self.records, self.timestamps):
+                flags = int(r["flags"])
+                out.append(Candidate(
+                    chunk=int(r["chunk"]), clip=self._clip_names[int(r["clip"])], peak=int(r["peak"]),
+                    kind=_lib.KINDS[(flags >> _lib.KIND_SHIFT) & 3], accept=bool(flags & _lib.FLAG_ACCEPT),
+                    skipped=bool(flags & _lib.FLAG_SKIPPED), height=float(r["height"]),
+                    similarity_whole=float(r["similarity_whole"]), similarity_middle=float(r["similarity_middle"]),
+                    pearson=tuple(float(v) for v in r["pearson"]),
+                    tone=tuple(tuple(float(v) for v in seg) for seg in r["tone"]), timestamp=float(t)))
+            self._candidates = out
+        return self._candidates
 
 
 def _torch():
@@ -134,6 +170,8 @@ class AudioPatternDetector:
         self._tone_frequencies: dict[str, float] = {}
         self._clip_lengths = [len(c.audio) for c in audio_clips]
         self._sliding_windows = [math.ceil(n / sr) for n in self._clip_lengths]
+        self._sw_arr = np.asarray(self._sliding_windows, dtype=np.int64)
+        self._clip_seconds_arr = np.asarray([n / sr for n in self._clip_lengths], dtype=np.float64)
         self._chunk_samples = int(seconds_per_chunk * sr)
         self._chunk_size = self._chunk_samples * 4                         # reference :224
 
@@ -269,18 +307,21 @@ class AudioPatternDetector:
         return n.value
 
     # ------------------------------------------------------------------ timestamps
-    def _timestamp(self, peak: int, chunk: int, clip_index: int) -> float:
-        """reference :585 then :440-451, same order of float operations."""
+    def _timestamps(self, rec: "NDArray[Any]") -> "NDArray[np.float64]":
+        """reference :585 then :440-451, same order of float64 operations, for a whole candidate table."""
         sr = self.target_sample_rate
-        t = peak / sr
-        t = t - (self._sliding_windows[clip_index] if chunk > 0 else 0)
-        t = t + (chunk * self.seconds_per_chunk)
-        t = t - (self._clip_lengths[clip_index] / sr)
-        return t if t >= 0 else 0
+        clip = rec["clip"]
+        chunk = rec["chunk"].astype(np.int64)
+        t = rec["peak"].astype(np.float64) / sr
+        t = t - np.where(chunk > 0, self._sw_arr[clip], 0).astype(np.float64)
+        t = t + (chunk * int(self.seconds_per_chunk)).astype(np.float64)
+        t = t - self._clip_seconds_arr[clip]
+        return np.where(t >= 0, t, 0.0)
 
-    # ------------------------------------------------------------------ device scan of one batch
+    # ------------------------------------------------------------------ device scan of a chunk range
     def _scan_batch(self, dev_ptr: int, base_sample: int, n_samples: int, chunk_begin: int, chunk_end: int,
-                    want_trace: bool) -> tuple[list[Candidate], Optional[dict]]:
+                    want_trace: bool) -> tuple["NDArray[Any]", Optional[dict]]:
+        """One apd_scan over chunks [chunk_begin, chunk_end); returns (candidate table, unit trace)."""
         torch = _torch()
         L = _lib.lib()
         nb = chunk_end - chunk_begin
@@ -296,17 +337,7 @@ class AudioPatternDetector:
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(L.apd_scan(self._ctx, C.c_void_p(dev_ptr), base_sample, n_samples, chunk_begin, chunk_end,
                               cands, cap, C.byref(n), trace, lufs, C.c_void_p(stream)), "apd_scan")
-        out: list[Candidate] = []
-        for i in range(n.value):
-            r = cands[i]
-            kind = _lib.KINDS[(r.flags >> _lib.KIND_SHIFT) & 3]
-            out.append(Candidate(chunk=r.chunk, clip=self.audio_clips[r.clip].name, peak=r.peak, kind=kind,
-                                 accept=bool(r.flags & _lib.FLAG_ACCEPT), skipped=bool(r.flags & _lib.FLAG_SKIPPED),
-                                 height=r.height, similarity_whole=r.similarity_whole,
-                                 similarity_middle=r.similarity_middle, pearson=tuple(r.pearson),
-                                 tone=tuple(tuple(seg) for seg in r.tone),
-                                 timestamp=self._timestamp(r.peak, r.chunk, r.clip)))
-            out[-1]._clip_index = r.clip  # type: ignore[attr-defined]
+        rec = np.frombuffer(cands, dtype=CAND_DTYPE, count=n.value).copy()
         tr = None
         if want_trace:
             tr = {}
@@ -316,26 +347,27 @@ class AudioPatternDetector:
                     tr[(chunk_begin + ci, self.audio_clips[p].name)] = {
                         "absmax": u.absmax, "max_choose": u.max_choose, "n_out": u.n_out,
                         "n_peaks": u.n_peaks, "lufs": lufs[ci * ncl + p]}
-        return out, tr
+        return rec, tr
 
-    def _emit_batch(self, cands: list[Candidate], chunk_begin: int, chunk_end: int,
+    def _emit_batch(self, rec: "NDArray[Any]", ts: "NDArray[np.float64]",
                     peak_times: Optional[dict[str, list[float]]], events: list[tuple[float, str]],
                     on_pattern_detected: Optional[PatternDetectedCallback]) -> None:
-        """Per chunk: clips in list order, then a stable sort by timestamp (reference :303-327)."""
-        by_chunk: dict[int, list[Candidate]] = {}
-        for c in cands:
-            if c.accept:
-                by_chunk.setdefault(c.chunk, []).append(c)
-        for i in range(chunk_begin, chunk_end):
-            hits = by_chunk.get(i, [])               # already ordered by (clip index, peak)
-            if peak_times is not None:
-                for c in hits:
-                    peak_times[c.clip].append(c.timestamp)
-            ordered = sorted(((c.timestamp, c.clip) for c in hits), key=lambda e: e[0])
-            for t, name in ordered:
-                events.append((t, name))
-                if on_pattern_detected:
-                    on_pattern_detected(name, t)
+        """Accepted candidates -> results, in the reference's order (:303-327): per chunk the clips in list
+        order (the table is ordered by chunk, clip, peak), then a stable sort by timestamp inside the chunk."""
+        acc = np.flatnonzero(rec["flags"] & _lib.FLAG_ACCEPT)
+        if acc.size == 0:
+            return
+        names = [c.name for c in self.audio_clips]
+        clip = rec["clip"][acc]
+        t = ts[acc]
+        if peak_times is not None:
+            for k, tv in zip(clip.tolist(), t.tolist()):
+                peak_times[names[k]].append(tv)
+        order = np.lexsort((t, rec["chunk"][acc]))          # stable: ties keep (clip, peak) order
+        for k, tv in zip(clip[order].tolist(), t[order].tolist()):
+            events.append((tv, names[k]))
+            if on_pattern_detected:
+                on_pattern_detected(names[k], tv)
 
     # ------------------------------------------------------------------ public scanning API
     def scan_array(self, audio: "NDArray[np.float32] | Any", on_pattern_detected: Optional[PatternDetectedCallback] = None,
@@ -376,7 +408,8 @@ class AudioPatternDetector:
             raise ValueError("slab ends inside a chunk that is not the stream's last")
         peak_times: dict[str, list[float]] = {c.name: [] for c in self.audio_clips}
         events: list[tuple[float, str]] = []
-        all_cands: list[Candidate] = []
+        all_rec: list[Any] = []
+        all_ts: list[Any] = []
         trace: Optional[dict] = {} if collect_trace else None
         with torch.cuda.device(self._device):
             # one apd_scan per segment: the C side cuts a segment into sub-batches of max_batch_chunks chunks
@@ -406,16 +439,19 @@ class AudioPatternDetector:
                     torch.cuda.current_stream().wait_event(ready[si])
                     if si + 2 < len(bounds):
                         enqueue_copy(bounds[si + 2])
-                cands, tr = self._scan_batch(dev.data_ptr(), base_sample, n, c0, c1, collect_trace)
-                all_cands.extend(cands)
+                rec, tr = self._scan_batch(dev.data_ptr(), base_sample, n, c0, c1, collect_trace)
+                ts = self._timestamps(rec)
+                all_rec.append(rec)
+                all_ts.append(ts)
                 if trace is not None and tr:
                     trace.update(tr)
-                self._emit_batch(cands, c0, c1, peak_times, events, on_pattern_detected)
+                self._emit_batch(rec, ts, peak_times, events, on_pattern_detected)
         total = 0.0
         for i in range(first, last):                                        # reference :301
             total += (min((i + 1) * C_, end_sample) - i * C_) / self.target_sample_rate
-        return ScanResult(peak_times=peak_times, events=events, candidates=all_cands, unit_trace=trace,
-                          total_time=total)
+        records = np.concatenate(all_rec) if all_rec else np.zeros(0, dtype=CAND_DTYPE)
+        stamps = np.concatenate(all_ts) if all_ts else np.zeros(0, dtype=np.float64)
+        return ScanResult(peak_times, events, records, stamps, [c.name for c in self.audio_clips], trace, total)
 
     def find_clip_in_audio(self, audio_stream: AudioStream,
                            on_pattern_detected: PatternDetectedCallback | None = None,
@@ -470,8 +506,8 @@ class AudioPatternDetector:
                 host[n_halo:] = new
                 self._dev_buf[:n_tot].copy_(self._pinned[:n_tot], non_blocking=True)
                 c0, c1 = chunk_index, chunk_index + len(parts)
-                cands, _ = self._scan_batch(self._dev_buf.data_ptr(), c0 * C_ - n_halo, n_tot, c0, c1, False)
-                self._emit_batch(cands, c0, c1, peak_times, events, on_pattern_detected)
+                rec, _ = self._scan_batch(self._dev_buf.data_ptr(), c0 * C_ - n_halo, n_tot, c0, c1, False)
+                self._emit_batch(rec, self._timestamps(rec), peak_times, events, on_pattern_detected)
                 keep = min(self._max_halo, n_tot)
                 halo = host[n_tot - keep:n_tot].copy()
                 chunk_index = c1

@@ -446,7 +446,9 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
                      int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st)
 {
     static const int per_max = std::max(1, env_int2("APD_B200_PER", 16));
-    static const int keep_h = env_int2("APD_B200_KEEP_H", 1);
+    // 0: both operands re-read per unit (80 registers, 3 CTAs/SM); 1: the clip row stays in registers (128 registers,
+    // 2 CTAs/SM).  Equal alone; the smaller CTAs lose less when phase-2 CTAs share the SMs.
+    static const int keep_h = env_int2("APD_B200_KEEP_H", 0);
     static const int swap = env_int2("APD_B200_SWAP", 1);
     static const int lag = std::max(1, env_int2("APD_B200_FUSED_LAG", 1));
     static const int slots = std::max(lag + 1, env_int2("APD_B200_FUSED_SLOTS", 4));

@@ -94,20 +94,37 @@ __device__ __forceinline__ void mat4_apply_add(const double* __restrict__ Mx, co
         s[r] += Mx[r * 4 + 0] * t[0] + Mx[r * 4 + 1] * t[1] + Mx[r * 4 + 2] * t[2] + Mx[r * 4 + 3] * t[3];
 }
 
-// One warp per union section: turns zero-state end states into carry-in states, in place.
-__global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int cells_stride, double* __restrict__ state)
+__device__ __forceinline__ void mat4_vec(const double* __restrict__ Mx, const double t[4], double r[4])
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= nsec) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        r[i] = Mx[i * 4 + 0] * t[0] + Mx[i * 4 + 1] * t[1] + Mx[i * 4 + 2] * t[2] + Mx[i * 4 + 3] * t[3];
+}
+
+// One CTA of kScanWarps warps per union section: turns zero-state end states into carry-in states, in
+// place.  The cells are cut into one contiguous slice per warp; each warp scans its slice from zero state
+// (32 cells per step: warp scan with the transition powers Mc^1..Mc^32), the slice carries are chained by
+// one thread (c_{w+1} = Mc^{cells of slice w} c_w + e_w), and a second sweep adds Mc^{cells since the slice
+// start} c_w to every cell.
+constexpr int kScanWarps = 8;
+
+__global__ void __launch_bounds__(kScanWarps * 32)
+k_kw_scan(KwConfig K, SectionGeom G, int nsec, int cells_stride, double* __restrict__ state)
+{
+    __shared__ double s_end[kScanWarps][4];      // slice end state from zero carry-in, then the slice carry-in
+    const int sec = blockIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long start;
     int n;
-    section_bounds(G, warp, start, n);
+    section_bounds(G, sec, start, n);
     const int ncells = (n + K.cell - 1) / K.cell;
-    double* st = state + (long long)warp * cells_stride * 4;
+    const int ngroups = (ncells + 31) / 32;
+    const int gper = (ngroups + kScanWarps - 1) / kScanWarps;
+    const int g_lo = w * gper, g_hi = min(ngroups, g_lo + gper);
+    double* st = state + (long long)sec * cells_stride * 4;
     double prev[4] = {0, 0, 0, 0};                           // state at the start of this group of 32 cells
-    for (int g0 = 0; g0 < ncells; g0 += 32) {
-        const int i = g0 + lane;
+    for (int g = g_lo; g < g_hi; ++g) {
+        const int i = g * 32 + lane;
         double s[4] = {0, 0, 0, 0};
         if (i < ncells) { s[0] = st[i * 4]; s[1] = st[i * 4 + 1]; s[2] = st[i * 4 + 2]; s[3] = st[i * 4 + 3]; }
 #pragma unroll
@@ -127,6 +144,44 @@ __global__ void k_kw_scan(KwConfig K, SectionGeom G, int nsec, int cells_stride,
         if (i < ncells) { st[i * 4] = c[0]; st[i * 4 + 1] = c[1]; st[i * 4 + 2] = c[2]; st[i * 4 + 3] = c[3]; }
 #pragma unroll
         for (int r = 0; r < 4; ++r) prev[r] = __shfl_sync(0xffffffffu, s[r], 31);
+    }
+    if (lane == 0) { s_end[w][0] = prev[0]; s_end[w][1] = prev[1]; s_end[w][2] = prev[2]; s_end[w][3] = prev[3]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // T = Mc^(32 * gper) by repeated multiplication with Mc^32 (a full slice; only the last one can be shorter)
+        double T[16], c[4] = {0, 0, 0, 0};
+        const double* M32 = K.mpow + 31 * 16;
+        for (int e = 0; e < 16; ++e) T[e] = (e % 5 == 0) ? 1.0 : 0.0;
+        for (int p = 0; p < gper; ++p) {
+            double U[16];
+            for (int r = 0; r < 4; ++r)
+                for (int cc = 0; cc < 4; ++cc) {
+                    double acc = 0;
+                    for (int q = 0; q < 4; ++q) acc += M32[r * 4 + q] * T[q * 4 + cc];
+                    U[r * 4 + cc] = acc;
+                }
+            for (int e = 0; e < 16; ++e) T[e] = U[e];
+        }
+        for (int ww = 0; ww < kScanWarps; ++ww) {
+            const double e[4] = {s_end[ww][0], s_end[ww][1], s_end[ww][2], s_end[ww][3]};
+            s_end[ww][0] = c[0]; s_end[ww][1] = c[1]; s_end[ww][2] = c[2]; s_end[ww][3] = c[3];
+            double nx[4];
+            mat4_vec(T, c, nx);
+            for (int r = 0; r < 4; ++r) c[r] = nx[r] + e[r];
+        }
+    }
+    __syncthreads();
+    if (w == 0) return;                                       // the first slice starts from the true zero state
+    double d[4] = {s_end[w][0], s_end[w][1], s_end[w][2], s_end[w][3]};       // Mc^(32 gi) c_w
+    for (int g = g_lo; g < g_hi; ++g) {
+        const int i = g * 32 + lane;
+        double add[4] = {d[0], d[1], d[2], d[3]};
+        if (lane > 0) mat4_vec(K.mpow + (lane - 1) * 16, d, add);             // Mc^lane d
+        if (i < ncells) { st[i * 4] += add[0]; st[i * 4 + 1] += add[1]; st[i * 4 + 2] += add[2]; st[i * 4 + 3] += add[3]; }
+        double nd[4];
+        mat4_vec(K.mpow + 31 * 16, d, nd);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) d[r] = nd[r];
     }
 }
 
@@ -393,7 +448,7 @@ void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom
     const int ncells = (nmax + K.cell - 1) / K.cell;
     dim3 grid((ncells + 127) / 128, nsec);
     k_kw_cells<0><<<grid, 128, smem, st>>>(K, Gu, cells_stride, state, energy, energy_m1);
-    k_kw_scan<<<(nsec * 32 + 127) / 128, 128, 0, st>>>(K, Gu, nsec, cells_stride, state);
+    k_kw_scan<<<nsec, kScanWarps * 32, 0, st>>>(K, Gu, nsec, cells_stride, state);
     k_kw_cells<1><<<grid, 128, smem, st>>>(K, Gu, cells_stride, state, energy, energy_m1);
     if (need_patch) k_kw_patch<<<(nsec * G * 32 + 127) / 128, 128, 0, st>>>(K, Gu, d_geoms, nsec, G, patch);
     k_kw_gate<<<(nsec * G * 32 + 127) / 128, 128, 0, st>>>(K, Gu, d_geoms, nsec, G, cells_stride, energy, energy_m1,

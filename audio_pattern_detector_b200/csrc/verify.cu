@@ -619,31 +619,41 @@ __device__ __forceinline__ bool is_tone_slot(const VerifyArgs& A, int s)
     return A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0;
 }
 
-// Ordered gather of the per-slot records (normal / short clips) into the output list.
-__global__ void __launch_bounds__(256)
+// Ordered gather of the per-slot records (normal / short clips) into the output list: one thread per slot
+// reads its count, block-wide exclusive scan, then one warp per slot copies its records.
+__global__ void __launch_bounds__(1024)
 k_emit(VerifyArgs A, int nslots)
 {
-    __shared__ int s_off[1025];
-    if (threadIdx.x == 0) {
-        int off = *A.out_count;
-        for (int s = 0; s < nslots; ++s) {
-            s_off[s] = off;
-            if (A.pk.slot0 + s < *A.pk.sel_count && !is_tone_slot(A, s)) off += A.pk.n_peaks[s];
-        }
-        s_off[nslots] = off;
+    __shared__ int s_off[kMaxSlots + 1];
+    __shared__ int s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nsel = *A.pk.sel_count;
+    const int base = *A.out_count;
+    int cnt = 0;
+    if (t < nslots && A.pk.slot0 + t < nsel && !is_tone_slot(A, t)) cnt = A.pk.n_peaks[t];
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
     }
+    if (lane == 31) s_warp[w] = inc;
     __syncthreads();
-    for (int s = 0; s < nslots; ++s) {
-        if (A.pk.slot0 + s >= *A.pk.sel_count) break;
-        if (is_tone_slot(A, s)) continue;
-        const int np = A.pk.n_peaks[s];
-        for (int p = threadIdx.x; p < np; p += blockDim.x) {
-            const int o = s_off[s] + p;
-            if (o < A.out_capacity) A.out[o] = A.slot_cands[(long long)s * A.pk.peak_stride + p];
+    int woff = 0;
+    for (int k = 0; k < w; ++k) woff += s_warp[k];
+    if (t < nslots) s_off[t] = base + woff + inc - cnt;
+    if (t == nslots - 1) s_off[nslots] = base + woff + inc;
+    __syncthreads();
+    for (int s = w; s < nslots; s += (int)(blockDim.x >> 5)) {
+        const int np = s_off[s + 1] - s_off[s];
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(A.slot_cands + (long long)s * A.pk.peak_stride);
+        constexpr int Q = (int)(sizeof(apd_candidate) / sizeof(uint4));
+        for (int i = lane; i < np * Q; i += 32) {
+            const int o = s_off[s] + i / Q;
+            if (o < A.out_capacity) reinterpret_cast<uint4*>(A.out + o)[i % Q] = src[i];
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (t == 0) {
         if (s_off[nslots] > A.out_capacity) atomicOr(A.pk.overflow, 4);
         *A.out_count = s_off[nslots] < A.out_capacity ? s_off[nslots] : A.out_capacity;
     }
@@ -706,7 +716,7 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
 void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
 {
     if (nslots <= 0) return;
-    k_emit<<<1, 256, 0, st>>>(A, nslots);
+    k_emit<<<1, 1024, 0, st>>>(A, nslots);     // nslots <= kMaxSlots == 1024
     ++*launches;
 }
 

@@ -260,7 +260,7 @@ def main() -> None:
                        "l2": "inputs (2.8 GB/GPU) larger than L2; no flush needed",
                        "detections_per_step": n_det, "planted": len(plants)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 4),
-                    "d2h_bytes_per_step": int(len(res.candidates) * 176 + n_chunks // args.batch_chunks * 64),
+                    "d2h_bytes_per_step": int(res.n_candidates * 176 + n_chunks // args.batch_chunks * 64),
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
