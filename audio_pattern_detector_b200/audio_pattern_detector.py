@@ -414,8 +414,13 @@ class AudioPatternDetector:
         with torch.cuda.device(self._device):
             # one apd_scan per segment: the C side cuts a segment into sub-batches of max_batch_chunks chunks
             # and overlaps phase 2 of one sub-batch with phase 1 of the next
-            seg = self._max_batch * 8 if host is not None else max(last - first, 1)
-            bounds = list(range(first, last, seg)) + [last]
+            if host is not None:
+                # a short first segment (its copy is the only one not hidden), then long ones
+                seg = self._max_batch * 8
+                head = min(last, first + self._max_batch)
+                bounds = [first] + list(range(head, last, seg)) + [last] if head < last else [first, last]
+            else:
+                bounds = [first, last]
             copied = 0                                   # slab samples already enqueued for copy
             copy_stream = torch.cuda.Stream() if host is not None else None
             ready: list[Any] = []

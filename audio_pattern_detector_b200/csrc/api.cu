@@ -958,7 +958,8 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    phase2_tone(c, c->h_counts[S + 3], st);
+    static const bool skip_tone = getenv("APD_B200_SKIP_TONE") && atoi(getenv("APD_B200_SKIP_TONE"));   // timing experiments
+    if (!skip_tone) phase2_tone(c, c->h_counts[S + 3], st);
     if (c->profile) cudaEventRecord(c->ev[6], st);
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

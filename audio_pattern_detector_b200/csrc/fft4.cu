@@ -260,7 +260,8 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restric
     constexpr int T1 = N1 / 8;
     constexpr int R2 = S::R2;
     constexpr int NLAST = N1 / R2;
-    __shared__ __align__(1024) c2 raw[N1 * TB + ColLayout<TB>::SLACK];
+    extern __shared__ __align__(1024) unsigned char fwd_cols_smem[];           // two exchange buffers (dynamic: > 48 KB for TB = 8)
+    c2* raw = reinterpret_cast<c2*>(fwd_cols_smem);
     const int q = threadIdx.x % TB, j = threadIdx.x / TB;
     const int bcol = blockIdx.x * TB + q;
     const int M = P.M;
@@ -278,7 +279,12 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restric
     }
     const int m_lo = j * kRowN + bcol;                       // first-pass input r: m = m_lo + r * T1 * 512
     const int t_end = min(ntr, (int)(blockIdx.y + 1) * per);
-    for (int t = blockIdx.y * per; t < t_end; ++t) {
+    constexpr unsigned kBufB = N1 * TB * 8u;                 // second exchange buffer (pass 2 -> 3)
+    // software pipeline: the raw samples (and gain) of transform t + 1 are requested right after the first
+    // exchange of transform t
+    float x0[8], x1[8];
+    double gain = 1.0;
+    auto fetch = [&](int t) {
         const int sec = FG.ng ? t / FG.ng : t;
         int gcol = 0;
         if (FG.ng) {
@@ -290,36 +296,37 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restric
         int n;
         section_bounds(G, sec, start, n);
         const float* __restrict__ x = G.audio + (start - G.base) + m_lo;
-        const double gain = gains ? gains[(long long)sec * gain_stride + gcol] : 1.0;
-        c2 v[R2 > 8 ? R2 : 8];
-        float x0[8], x1[8];
+        gain = gains ? gains[(long long)sec * gain_stride + gcol] : 1.0;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int m = m_lo + r * T1 * kRowN;
             x0[r] = m < n ? x[r * T1 * kRowN] : 0.0f;
             x1[r] = m + M < n ? x[r * T1 * kRowN + M] : 0.0f;
         }
+    };
+    if ((int)(blockIdx.y * per) < t_end) fetch(blockIdx.y * per);
+    for (int t = blockIdx.y * per; t < t_end; ++t) {
+        c2 v[R2 > 8 ? R2 : 8];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
             v[r] = cmul(mk(normalize_sample(x0[r], gain), -normalize_sample(x1[r], gain)), pre[r]);
         Dft2<8, -1>::run(v);
         col_store1<TB>(A, v);
+        if (t + 1 < t_end) fetch(t + 1);
         __syncthreads();
         ColLoad<TB, T1, 8>::run(A, v);
-        __syncthreads();
         bfly_tw<8>(v, tw2);
         Dft2<8, -1>::run(v);
-        col_store2<TB>(A, v);
+        col_store2<TB, kBufB>(A, v);
         __syncthreads();
         if (N1 == 512 || j < NLAST) {
-            ColLoad<TB, 64, R2>::run(A, v);
+            ColLoad<TB, 64, R2, kBufB>::run(A, v);
             bfly_tw<R2>(v, tw3);
             Dft2<R2, -1>::run(v);
             c2* __restrict__ out = reinterpret_cast<c2*>(T + (long long)t * M + (long long)j * kRowN + bcol);
 #pragma unroll
             for (int r = 0; r < R2; ++r) out[(long long)r * NLAST * kRowN] = cmul(v[r], fs[r]);
         }
-        __syncthreads();
     }
 }
 
@@ -348,10 +355,18 @@ static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G
                                  cudaStream_t st)
 {
     dim3 gc(P.N2 / TB, ny);
+    const size_t sm512 = (size_t)(2 * 512 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
+    const size_t sm640 = (size_t)(2 * 640 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_fwd_cols_fast<Shape512, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm512);
+        cudaFuncSetAttribute(k_fwd_cols_fast<Shape640, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm640);
+        attr = true;
+    }
     if (fs == 512)
-        k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, 0, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
+        k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, sm512, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
     else
-        k_fwd_cols_fast<Shape640, TB><<<gc, TB * 80, 0, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
+        k_fwd_cols_fast<Shape640, TB><<<gc, TB * 80, sm640, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
 }
 
 static int fast_shape(const Fft4Plan& P)
