@@ -421,6 +421,8 @@ class AudioPatternDetector:
                 bounds = [first] + list(range(head, last, seg)) + [last] if head < last else [first, last]
             else:
                 bounds = [first, last]
+            if last <= first:
+                bounds = [first]
             copied = 0                                   # slab samples already enqueued for copy
             copy_stream = torch.cuda.Stream() if host is not None else None
             ready: list[Any] = []

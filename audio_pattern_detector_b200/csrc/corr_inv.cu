@@ -15,6 +15,8 @@
 // the last pass straight to the epilogue.  All twiddles and all shared-memory addresses are loop
 // invariants of the per-CTA loop over units: the XOR-swizzled exchange layouts (fft_fast.cuh) reduce to
 // "thread constant + immediate" for loads and "thread constant ^ immediate" for stores.
+#include <cmath>
+
 #include "fft_fast.cuh"
 #include "internal.h"
 
@@ -341,6 +343,134 @@ k_corr_cols(const UnitDesc* __restrict__ D, int nunits, int per, int M, const fl
                         WRITE ? corr + (long long)u0 * corr_stride : nullptr, corr_stride);
 }
 
+// ---------------------------------------------------------------- columns, two per thread (phase 1)
+// Same pass structure as cols_item, but a thread owns the butterflies j of TWO adjacent columns: the exchange
+// moves 16 bytes per instruction (the pair is adjacent in the swizzled layout, still conflict-free), the W
+// column pair is one 16-byte global load, the twiddles are shared by the two butterflies, and a CTA executes
+// twice the arithmetic between barriers.  The column-dependent part of the post-twiddle differs between the
+// two columns by e^{i pi / N}; it is folded into per-output constants kept in constant memory.
+__constant__ float2 c_post[2][2][10];        // [shape: 512, 640][column of the pair][r] = e^{i pi (r / (2 R2) + col / N)}
+
+__device__ __forceinline__ void ldg_l2_x2(const c2* p, c2& x, c2& y)
+{
+    asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(x.v), "=l"(y.v) : "l"(p) : "memory");
+}
+
+template <class S>
+__device__ __forceinline__ void cols2_item(c2* raw, float* red, const UnitDesc* __restrict__ D, int u_begin, int u_end,
+                                           int tile, int M, const float2* __restrict__ Wg,
+                                           unsigned int* __restrict__ unit_max_bits)
+{
+    constexpr int N1 = S::N;
+    constexpr int T1 = N1 / 8;
+    constexpr int R2 = S::R2;
+    constexpr int NLAST = N1 / R2;
+    constexpr int NW = 2 * T1 / 32;                          // warps per CTA (4 or 5)
+    constexpr int SH = N1 == 512 ? 0 : 1;
+    constexpr unsigned kBufB = N1 * kTB * 8u;
+    const int p = threadIdx.x & 1, j = threadIdx.x >> 1;
+    const int bcol = tile * kTB + 2 * p;                     // first column of the pair
+    const ColAddr<kTB> A(raw, j, 2 * p);
+    float2 tw2[8], tw3[R2];
+    pass_twiddles<8, +1, 8>(j, tw2);
+    pass_twiddles<R2, +1, 64>(j, tw3);
+    {
+        const float invN = 1.0f / (2.0f * (float)M);
+        const float invM = 1.0f / (float)M;
+        const float2 base = cispif((float)((j % NLAST) * kN2 + bcol) * invN);
+        const float2 sbase = make_float2(base.x * invM, base.y * invM);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) tw3[r] = cmul(tw3[r], sbase);
+    }
+    const long long col_off = (long long)j * kN2 + bcol;
+    const int m0 = (j % NLAST) * kN2 + bcol;
+    int pending = -1, parity = 0;
+    c2 na[8], nb[8];
+    UnitDesc dn = load_desc(D + u_begin);
+    if (dn.n_out >= 0) {
+        const c2* __restrict__ in = reinterpret_cast<const c2*>(Wg + col_off);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ldg_l2_x2(in + (long long)T1 * kN2 * r, na[r], nb[r]);
+    }
+    for (int u = u_begin; u < u_end; ++u) {
+        const UnitDesc d = dn;
+        const bool more = u + 1 < u_end;
+        if (more) dn = load_desc(D + u + 1);
+        const c2* __restrict__ in_next = reinterpret_cast<const c2*>(Wg + (long long)(u + 1 - u_begin) * M + col_off);
+        if (d.n_out < 0) {
+            if (more && dn.n_out >= 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) ldg_l2_x2(in_next + (long long)T1 * kN2 * r, na[r], nb[r]);
+            }
+            continue;
+        }
+        c2 va[R2 > 8 ? R2 : 8], vb[R2 > 8 ? R2 : 8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { va[r] = na[r]; vb[r] = nb[r]; }
+        Dft2<8, +1>::run(va);
+        Dft2<8, +1>::run(vb);
+        col_store1_x2<kTB>(A, va, vb);
+        if (more && dn.n_out >= 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ldg_l2_x2(in_next + (long long)T1 * kN2 * r, na[r], nb[r]);
+        }
+        __syncthreads();
+        if (pending >= 0 && threadIdx.x < 32) {
+            float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
+        }
+        ColLoad2<kTB, T1, 8>::run(A, va, vb);
+        bfly_tw<8>(va, tw2);
+        bfly_tw<8>(vb, tw2);
+        Dft2<8, +1>::run(va);
+        Dft2<8, +1>::run(vb);
+        col_store2_x2<kTB, kBufB>(A, va, vb);
+        __syncthreads();
+        float best = 0.0f;
+        if (N1 == 512 || j < NLAST) {
+            ColLoad2<kTB, 64, R2, kBufB>::run(A, va, vb);
+#pragma unroll
+            for (int r = 0; r < R2; ++r) { va[r] = cmul(va[r], tw3[r]); vb[r] = cmul(vb[r], tw3[r]); }
+            Dft2<R2, +1>::run(va);
+            Dft2<R2, +1>::run(vb);
+            const int lim0 = d.n_out - m0, lim1 = d.n_out - M - m0;      // column a valid iff 32768 r < lim; b: + 1
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                float ar, ai, br, bi;
+                split(cmul(va[r], c_post[SH][0][r]), ar, ai);
+                split(cmul(vb[r], c_post[SH][1][r]), br, bi);
+                if (64 * kN2 * r < lim0) best = fmaxf(best, fabsf(ar));
+                if (64 * kN2 * r < lim1) best = fmaxf(best, fabsf(ai));
+                if (64 * kN2 * r + 1 < lim0) best = fmaxf(best, fabsf(br));
+                if (64 * kN2 * r + 1 < lim1) best = fmaxf(best, fabsf(bi));
+            }
+        }
+        best = warp_max(best);
+        if ((threadIdx.x & 31) == 0) red[parity * NW + (threadIdx.x >> 5)] = best;
+        pending = d.max_idx;
+        parity ^= 1;
+    }
+    __syncthreads();
+    if (pending >= 0 && threadIdx.x < 32) {
+        float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+        t = warp_max(t);
+        if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
+    }
+}
+
+template <class S>
+__global__ void __launch_bounds__(2 * (S::N / 8), S::N == 512 ? 4 : 3)
+k_corr_cols2(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
+             unsigned int* __restrict__ unit_max_bits, int swap)
+{
+    __shared__ __align__(1024) c2 raw[2 * S::N * kTB + ColLayout<kTB>::SLACK];
+    __shared__ float red[2 * (2 * (S::N / 8) / 32)];
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int u0 = by * per;
+    cols2_item<S>(raw, red, D, u0, min(nunits, u0 + per), bx, M, W + (long long)u0 * M, unit_max_bits);
+}
+
 // ---------------------------------------------------------------- fused persistent kernel
 // Phase 1 (max only) as ONE persistent launch in which the four-step intermediate W never leaves L2.
 // Units are taken in groups of U; a group's row pass (128 items: 4 or 5 rows each) and column pass (128 items: 4
@@ -487,6 +617,26 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
     const dim3 gc = swap ? dim3(ny, col_tiles) : dim3(col_tiles, ny);
     if (keep_h) k_corr_rows<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     else k_corr_rows<false><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
+    static const int cols2 = env_int2("APD_B200_COLS2", 1);
+    if (cols2 && !write) {
+        static bool uploaded = false;
+        if (!uploaded) {
+            float2 h[2][2][10];
+            const int r2[2] = {8, 10};
+            const double n[2] = {2.0 * 512 * 512, 2.0 * 640 * 512};
+            for (int sh = 0; sh < 2; ++sh)
+                for (int col = 0; col < 2; ++col)
+                    for (int r = 0; r < 10; ++r) {
+                        const double a = M_PI * ((double)r / (2.0 * r2[sh]) + (double)col / n[sh]);
+                        h[sh][col][r] = make_float2((float)cos(a), (float)sin(a));
+                    }
+            cudaMemcpyToSymbol(c_post, h, sizeof(h));
+            uploaded = true;
+        }
+        if (P.N1 == 512) k_corr_cols2<Shape512><<<gc, 128, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+        else k_corr_cols2<Shape640><<<gc, 160, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+        return;
+    }
     if (P.N1 == 512) {
         if (write) k_corr_cols<Shape512, true><<<gc, kTB * 64, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, out.corr, out.corr_stride, swap);
         else k_corr_cols<Shape512, false><<<gc, kTB * 64, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, out.corr, out.corr_stride, swap);

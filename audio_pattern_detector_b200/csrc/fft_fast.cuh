@@ -246,6 +246,41 @@ template <int TB, int T, int R, int OFF = 0> struct ColLoad {
         if (R == 10) { v[8] = one<8>(A); v[9] = one<9>(A); }
     }
 };
+// 128-bit variants: a thread owns two adjacent columns (q even), whose words are adjacent in the exchange buffer
+template <int OFF> __device__ __forceinline__ void lds128(unsigned a, c2& x, c2& y)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(x.v), "=l"(y.v) : "r"(a), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ void sts128(unsigned a, c2 x, c2 y)
+{
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(x.v), "l"(y.v) : "memory");
+}
+template <int TB, int T, int R, int OFF = 0> struct ColLoad2 {
+    template <int r> static __device__ __forceinline__ void one(const ColAddr<TB>& A, c2* va, c2* vb)
+    {
+        constexpr bool alt = (T == 80) && (ColLayout<TB>::SW == 3) && (r & 1);
+        lds128<OFF + 8 * TB * T * r>(alt ? A.ld_b : A.ld_a, va[r], vb[r]);
+    }
+    static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* va, c2* vb)
+    {
+        one<0>(A, va, vb); one<1>(A, va, vb); one<2>(A, va, vb); one<3>(A, va, vb);
+        one<4>(A, va, vb); one<5>(A, va, vb); one<6>(A, va, vb); one<7>(A, va, vb);
+        if (R == 10) { one<8>(A, va, vb); one<9>(A, va, vb); }
+    }
+};
+template <int TB, unsigned OFF = 0>
+__device__ __forceinline__ void col_store1_x2(const ColAddr<TB>& A, const c2* va, const c2* vb)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sts128((A.st1 + OFF) ^ (8u * TB * r), va[r], vb[r]);
+}
+template <int TB, unsigned OFF = 0>
+__device__ __forceinline__ void col_store2_x2(const ColAddr<TB>& A, const c2* va, const c2* vb)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sts128((A.st2 + OFF) ^ (8u * TB * (8 * r + (r & ColLayout<TB>::SW))), va[r], vb[r]);
+}
+
 template <int TB, unsigned OFF = 0> __device__ __forceinline__ void col_store1(const ColAddr<TB>& A, const c2* v)
 {
     static_assert(OFF % ColLayout<TB>::ALIGN == 0, "buffer offset must keep the store address alignment");
