@@ -631,7 +631,8 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         CK(dalloc(&b.d_gain, (size_t)B * G));
         CK(dalloc(&b.d_spec, (size_t)B * c->spec_slab));
     }
-    c->n_slots = 256;
+    c->n_slots = 128;                     // selected units per phase-2 round (further rounds if a batch selects more)
+    if (const char* e = getenv("APD_B200_SLOTS")) c->n_slots = std::min(std::max(8, atoi(e)), (int)kMaxSlots);
     c->inv_units = 512;
     if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
     {

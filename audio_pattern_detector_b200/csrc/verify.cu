@@ -50,16 +50,16 @@ __device__ __forceinline__ void init_record(apd_candidate& r, int chunk, int cli
 // normal + short clip
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_verify_normal(VerifyArgs A)
+k_verify_normal(VerifyArgs A, int nslots)
 {
     __shared__ double red[8];
     __shared__ double part[10];
     __shared__ float dsv[512];
-    const int slot = blockIdx.y;
-    if (A.pk.slot0 + slot >= *A.pk.sel_count) return;
+    const int nsel = *A.pk.sel_count;
+    for (int slot = blockIdx.y; slot < nslots && A.pk.slot0 + slot < nsel; slot += gridDim.y) {
     const int2 unit = A.pk.sel[A.pk.slot0 + slot];
     const int clip = unit.y;
-    if (A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0) return;
+    if (A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0) continue;
     long long start;
     int nsec;
     section_bounds(A.pk.geom[A.pk.clip_group[clip]], unit.x, start, nsec);
@@ -173,6 +173,7 @@ k_verify_normal(VerifyArgs A)
             if (accept) rec->flags |= APD_FLAG_ACCEPT;
         }
         __syncthreads();
+    }
     }
 }
 
@@ -353,15 +354,15 @@ k_tone_prep(VerifyArgs A, ToneRound T)
     const int r = blockIdx.z, seg = blockIdx.y;
     if (r >= T.n_round) return;
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= s.P) return;
-    double2 v = make_double2(0, 0);
-    if (n < s.L) {
-        const double xv = tone_sample(s, s.ms + n);
-        const double2 c = A.cv.tone_pre[s.clip][n];                 // hann * e^{-i pi n^2 / L}
-        v = make_double2(xv * c.x, xv * c.y);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < s.P; n += gridDim.x * blockDim.x) {
+        double2 v = make_double2(0, 0);
+        if (n < s.L) {
+            const double xv = tone_sample(s, s.ms + n);
+            const double2 c = A.cv.tone_pre[s.clip][n];             // hann * e^{-i pi n^2 / L}
+            v = make_double2(xv * c.x, xv * c.y);
+        }
+        tone_buf(T, r, seg, 0)[n] = v;
     }
-    tone_buf(T, r, seg, 0)[n] = v;
 }
 
 // One pass slot of the batched float64 FFT (see fft64 for the single-CTA variant used at init).
@@ -381,9 +382,8 @@ k_tone_fft_pass(VerifyArgs A, ToneRound T, int slot)
     double2* __restrict__ y = tone_buf(T, r, seg, (start_b + slot + 1) & 1);
     const double2* __restrict__ tw = A.cv.tone_tw[clip];
     const int half = P >> 1, quarter = P >> 2;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < quarter; j += gridDim.x * blockDim.x) {
     if (slot < r4) {
-        if (j >= quarter) return;
         const int Ns = 1 << (2 * slot);
         const int tstep = P / (4 * Ns);
         const int k = j & (Ns - 1);
@@ -410,6 +410,7 @@ k_tone_fft_pass(VerifyArgs A, ToneRound T, int slot)
             y[jj + half] = make_double2(a.x - b.x, a.y - b.y);
         }
     }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -419,10 +420,9 @@ k_tone_mul(VerifyArgs A, ToneRound T)
     if (r >= T.n_round) return;
     const int clip = T.items[T.i0 + r].clip;
     const int P = A.cv.tone_P[clip];
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= P) return;
     double2* f = tone_buf(T, r, seg, tone_npass(P) & 1);
-    f[n] = zmul(f[n], A.cv.tone_chirp_fft[clip][n]);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P; n += gridDim.x * blockDim.x)
+        f[n] = zmul(f[n], A.cv.tone_chirp_fft[clip][n]);
 }
 
 // One CTA per (segment, item): X_k = post[k] * conv[k] / P for k <= L/2 (conv ends in buffer A).
@@ -493,21 +493,21 @@ k_tone_frames(VerifyArgs A, ToneRound T)
         ftw[wl + t] = make_double2(wl > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(wl - 1)) : 1.0, 0.0);
     }
     __syncthreads();
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= work) return;
-    const int f = (int)(w / nbw), kb = (int)(w % nbw);
-    const int s0 = s.ms + f * hop;
-    double re = 0, im = 0;
-    int ph = 0;
-    for (int n = 0; n < wl; ++n) {
-        const double xw = tone_sample(s, s0 + n) * ftw[wl + n].x;
-        const double2 e = ftw[ph];
-        re += xw * e.x;
-        im += xw * e.y;
-        ph += kb;
-        if (ph >= wl) ph -= wl;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(w / nbw), kb = (int)(w % nbw);
+        const int s0 = s.ms + f * hop;
+        double re = 0, im = 0;
+        int ph = 0;
+        for (int n = 0; n < wl; ++n) {
+            const double xw = tone_sample(s, s0 + n) * ftw[wl + n].x;
+            const double2 e = ftw[ph];
+            re += xw * e.x;
+            im += xw * e.y;
+            ph += kb;
+            if (ph >= wl) ph -= wl;
+        }
+        ((double*)tone_buf(T, r, seg, 1))[w] = re * re + im * im;
     }
-    ((double*)tone_buf(T, r, seg, 1))[w] = re * re + im * im;
 }
 
 // Thread per frame: energy, dominant bin, band purity, "active" flag (du.py:89-105) into buffer A.
@@ -662,8 +662,9 @@ k_emit(VerifyArgs A, int nslots)
 void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
 {
     if (nslots <= 0) return;
-    dim3 gn(32, nslots);      // x: peaks of a unit in parallel (short clips can keep dozens); idle CTAs exit at once
-    k_verify_normal<<<gn, 256, 0, st>>>(A);
+    // x: peaks of a unit in parallel (short clips can keep dozens); y: slots, strided (most slots are unused)
+    dim3 gn(32, std::min(nslots, 32));
+    k_verify_normal<<<gn, 256, 0, st>>>(A, nslots);
     ++*launches;
 }
 
@@ -695,12 +696,15 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
         ToneRound T{(const ToneItem*)items, i0, std::min(round_items, n_items - i0), A.tone_scratch,
                     A.tone_scratch_stride, stats, metrics, wl, hop};
         const unsigned R = (unsigned)T.n_round;
-        k_tone_prep<<<dim3((max_P + 255) / 256, 3, R), 256, 0, st>>>(A, T);
+        // grid-stride in x (capping the grid at 32 CTAs per transform was measured: no gain for the correlate stage
+        // that shares the GPU, longer phase 2)
+        const unsigned gx = (unsigned)((max_P / 4 + 255) / 256);
+        k_tone_prep<<<dim3(gx, 3, R), 256, 0, st>>>(A, T);
         for (int s = 0; s < max_pass; ++s)
-            k_tone_fft_pass<false><<<dim3((max_P / 4 + 255) / 256, 3, R), 256, 0, st>>>(A, T, s);
-        k_tone_mul<<<dim3((max_P + 255) / 256, 3, R), 256, 0, st>>>(A, T);
+            k_tone_fft_pass<false><<<dim3(gx, 3, R), 256, 0, st>>>(A, T, s);
+        k_tone_mul<<<dim3(gx, 3, R), 256, 0, st>>>(A, T);
         for (int s = 0; s < max_pass; ++s)
-            k_tone_fft_pass<true><<<dim3((max_P / 4 + 255) / 256, 3, R), 256, 0, st>>>(A, T, s);
+            k_tone_fft_pass<true><<<dim3(gx, 3, R), 256, 0, st>>>(A, T, s);
         k_tone_stats<<<dim3(3, R), 1024, 0, st>>>(A, T);
         if (work_max > 0) {
             k_tone_frames<<<dim3((unsigned)((work_max + 255) / 256), 3, R), 256, (size_t)2 * wl * sizeof(double2), st>>>(A, T);
