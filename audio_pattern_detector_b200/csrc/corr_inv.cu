@@ -459,8 +459,8 @@ __device__ __forceinline__ void cols2_item(c2* raw, float* red, const UnitDesc* 
     }
 }
 
-template <class S>
-__global__ void __launch_bounds__(2 * (S::N / 8), S::N == 512 ? 4 : 3)
+template <class S, int MINB>
+__global__ void __launch_bounds__(2 * (S::N / 8), MINB)
 k_corr_cols2(const UnitDesc* __restrict__ D, int nunits, int per, int M, const float2* __restrict__ W,
              unsigned int* __restrict__ unit_max_bits, int swap)
 {
@@ -633,8 +633,14 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
             cudaMemcpyToSymbol(c_post, h, sizeof(h));
             uploaded = true;
         }
-        if (P.N1 == 512) k_corr_cols2<Shape512><<<gc, 128, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
-        else k_corr_cols2<Shape640><<<gc, 160, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+        static const int dense = env_int2("APD_B200_COLS2_DENSE", 0);      // one more CTA per SM (fewer registers)
+        if (P.N1 == 512) {
+            if (dense) k_corr_cols2<Shape512, 5><<<gc, 128, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+            else k_corr_cols2<Shape512, 4><<<gc, 128, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+        } else {
+            if (dense) k_corr_cols2<Shape640, 4><<<gc, 160, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+            else k_corr_cols2<Shape640, 3><<<gc, 160, 0, st>>>(D, nunits, per, P.M, scratch, out.unit_max_bits, swap);
+        }
         return;
     }
     if (P.N1 == 512) {
