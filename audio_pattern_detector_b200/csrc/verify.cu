@@ -49,10 +49,10 @@ __device__ __forceinline__ void init_record(apd_candidate& r, int chunk, int cli
 // ---------------------------------------------------------------------------
 // normal + short clip
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_verify_normal(VerifyArgs A, int nslots)
 {
-    __shared__ double red[8];
+    __shared__ double red[32];
     __shared__ double part[10];
     __shared__ float dsv[512];
     const int nsel = *A.pk.sel_count;
@@ -83,29 +83,29 @@ k_verify_normal(VerifyArgs A, int nslots)
         }
         const int beg = pk - (L - 1);                                      // au.py:177-191
         // max of the zero-padded slice
+        // (loads are made unconditional through a clamped index so that several are in flight per thread: these
+        //  loops run one CTA per peak and are otherwise bound by one L2 round trip per iteration)
         float m = 0.0f;
+#pragma unroll 8
         for (int t = threadIdx.x; t < W; t += blockDim.x) {
             const int k = beg + t;
-            if (k >= 0 && k < n) m = fmaxf(m, q[k]);
+            const float raw = q[min(max(k, 0), n - 1)];
+            if (k >= 0 && k < n) m = fmaxf(m, raw);
         }
         const float smax = block_max(m, red);
-        // partition MSEs (float32 element ops as numpy, float64 accumulation)
+        // partition MSEs (float32 element ops as numpy, float64 accumulation), one partition at a time
         const int ps = W / 10;
-        double acc[10];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) acc[i] = 0.0;
-        for (int t = threadIdx.x; t < ps * 10; t += blockDim.x) {
-            const int k = beg + t;
-            const float s = (k >= 0 && k < n) ? q[k] / smax : 0.0f / smax;
-            const float d = cc[t] - s;
-            const float d2 = d * d;
-            const int i = t / ps;
-#pragma unroll
-            for (int j = 0; j < 10; ++j)
-                if (j == i) acc[j] += (double)d2;
-        }
         for (int i = 0; i < 10; ++i) {
-            const double s = block_sum(acc[i], red);
+            double acc = 0.0;
+#pragma unroll 8
+            for (int t = i * ps + threadIdx.x; t < (i + 1) * ps; t += blockDim.x) {
+                const int k = beg + t;
+                const float raw = q[min(max(k, 0), n - 1)];
+                const float s = (k >= 0 && k < n) ? raw / smax : 0.0f / smax;
+                const float d = cc[t] - s;
+                acc += (double)(d * d);
+            }
+            const double s = block_sum(acc, red);
             if (threadIdx.x == 0) part[i] = s;
         }
         __syncthreads();
@@ -131,19 +131,22 @@ k_verify_normal(VerifyArgs A, int nslots)
                 const int nw = hi - lo;
                 const double step = (double)nw / (double)ds;               // lib.rs:289
                 __syncthreads();
-                for (int i = threadIdx.x; i < ds; i += blockDim.x) {
+                // one warp per output point, lanes striding through its window (coalesced)
+                for (int i = threadIdx.x >> 5; i < ds; i += (int)(blockDim.x >> 5)) {
                     int a = (int)((double)i * step);
                     int b = (int)((double)(i + 1) * step);
                     if (b <= a) b = a + 1;
                     if (a >= nw) a = nw - 1;
                     if (b > nw) b = nw;
                     float mx = -INFINITY;
-                    for (int t = a; t < b; ++t) {
+#pragma unroll 4
+                    for (int t = a + (int)(threadIdx.x & 31); t < b; t += 32) {
                         const int k = beg + lo + t;
-                        const float s = (k >= 0 && k < n) ? q[k] : 0.0f;
-                        mx = fmaxf(mx, s);
+                        const float raw = q[min(max(k, 0), n - 1)];
+                        mx = fmaxf(mx, (k >= 0 && k < n) ? raw : 0.0f);
                     }
-                    dsv[i] = mx / smax;
+                    mx = warp_max(mx);
+                    if ((threadIdx.x & 31) == 0) dsv[i] = mx / smax;
                 }
                 __syncthreads();
                 double sx = 0, sy = 0;
@@ -663,8 +666,8 @@ void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* 
 {
     if (nslots <= 0) return;
     // x: peaks of a unit in parallel (short clips can keep dozens); y: slots, strided (most slots are unused)
-    dim3 gn(32, std::min(nslots, 32));
-    k_verify_normal<<<gn, 256, 0, st>>>(A, nslots);
+    dim3 gn(32, std::min(nslots, 128));
+    k_verify_normal<<<gn, 1024, 0, st>>>(A, nslots);     // 1024 threads: a 10 s clip's slice is 160 k samples per pass
     ++*launches;
 }
 
