@@ -171,3 +171,19 @@ def test_planted_patterns_found_at_bench_scale():
     det2 = make_detector(pats, sr, spc, max_batch_chunks=3)
     res2 = det2.scan_array(audio.cpu().numpy())
     assert res2.peak_times == res.peak_times and res2.events == res.events
+
+
+def test_16khz_auto_chunk_many_patterns():
+    """BASELINE configs[3] shape at reduced length: 16 kHz, many patterns (0.3-10 s), auto chunk seconds
+    (2 * ceil(longest clip) = 20 s): planted clips are found at their planted samples."""
+    from audio_pattern_detector_b200 import workloads as W
+    sr = 16000
+    pats = W.make_patterns(40, sr, seed=7)
+    audio, plants = W.make_stream_device(600.0, pats, sr, seed=11, plants_per_pattern=1, chunk_seconds=20, device="cuda")
+    det = make_detector(pats, sr, None, max_batch_chunks=6)
+    assert det.seconds_per_chunk == 20
+    res = det.scan_array(audio)
+    found = {(n, int(round(t * sr))) for n, ts in res.peak_times.items() for t in ts}
+    missing = [(n, s0) for n, s0, _g in plants if (n, max(s0 - 1, 0)) not in found]
+    assert not missing, missing
+    assert sum(len(v) for v in res.peak_times.values()) <= len(plants) + 8
