@@ -249,7 +249,9 @@ struct apd_ctx {
     void* d_unit_desc2 = nullptr;
     cudaStream_t side = nullptr;          // phase 2
     cudaStream_t pre = nullptr;           // loudness of the next sub-batch (latency-bound, hidden under phase 1)
-    cudaEvent_t scan_start = nullptr;
+    cudaStream_t tone = nullptr;          // deferred marker-tone verification: bandwidth-heavy f64 FFT passes, at the
+                                          // caller's (low) priority so that they fill the tails of the correlate launches
+    cudaEvent_t scan_start = nullptr, tone_go = nullptr, tone_done = nullptr;
     struct BatchSet {
         float2* d_spec = nullptr;
         unsigned int* d_unit_max = nullptr;
@@ -663,6 +665,9 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         if (const char* e = getenv("APD_B200_PRIO")) if (!atoi(e)) hi = lo;
         CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&c->pre, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&c->tone, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&c->tone_go, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->tone_done, cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&c->scan_start, cudaEventDisableTiming));
     c->cur_set = 0;
@@ -729,6 +734,9 @@ extern "C" int apd_destroy(apd_ctx* c)
     }
     if (c->side) cudaStreamDestroy(c->side);
     if (c->pre) cudaStreamDestroy(c->pre);
+    if (c->tone) cudaStreamDestroy(c->tone);
+    if (c->tone_go) cudaEventDestroy(c->tone_go);
+    if (c->tone_done) cudaEventDestroy(c->tone_done);
     if (c->scan_start) cudaEventDestroy(c->scan_start);
     void* ptrs[] = {c->d_scratch2, c->d_unit_desc2,
                     c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_is_short, c->d_win_lo, c->d_win_hi,
@@ -960,7 +968,18 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         CK(cudaStreamSynchronize(st));
     }
     static const bool skip_tone = getenv("APD_B200_SKIP_TONE") && atoi(getenv("APD_B200_SKIP_TONE"));   // timing experiments
-    if (!skip_tone) phase2_tone(c, c->h_counts[S + 3], st);
+    if (!skip_tone && c->h_counts[S + 3] > 0) {
+        static const bool tone_low = !(getenv("APD_B200_TONE_LOW") && !atoi(getenv("APD_B200_TONE_LOW")));
+        if (tone_low && st == c->side) {
+            CK(cudaEventRecord(c->tone_go, st));
+            CK(cudaStreamWaitEvent(c->tone, c->tone_go, 0));
+            phase2_tone(c, c->h_counts[S + 3], c->tone);
+            CK(cudaEventRecord(c->tone_done, c->tone));
+            CK(cudaStreamWaitEvent(st, c->tone_done, 0));
+        } else {
+            phase2_tone(c, c->h_counts[S + 3], st);
+        }
+    }
     if (c->profile) cudaEventRecord(c->ev[6], st);
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
