@@ -36,7 +36,7 @@ logger = logging.getLogger(__name__)
 DEFAULT_SECONDS_PER_CHUNK = 60            # reference :33
 SHORT_CLIP_DURATION_THRESHOLD = 0.5       # reference :36
 MARKER_TONE_STRATEGY = "marker_tone"      # reference :38
-DEFAULT_BATCH_CHUNKS = 16
+DEFAULT_BATCH_CHUNKS = 32
 
 PatternDetectedCallback = Callable[[str, float], None]
 

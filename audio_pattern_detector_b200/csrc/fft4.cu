@@ -341,14 +341,6 @@ static int env_int(const char* name, int dflt)
 static int fast_tb() { static int v = env_int("APD_B200_TB", 8) == 4 ? 4 : 8; return v; }      // columns per forward CTA
 static int fast_per_max() { static int v = std::max(1, env_int("APD_B200_PER", 8)); return v; }  // transforms per CTA
 
-static int fast_per(int n)
-{
-    // keep at least ~8 CTAs per SM in the grid; otherwise amortise the twiddles over up to `per` transforms
-    int per = fast_per_max();
-    while (per > 1 && (long long)((n + per - 1) / per) * 64 < 148 * 8) per >>= 1;
-    return per;
-}
-
 template <int TB>
 static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G, const FwdGroups& FG,
                                  const double* gains, int gain_stride, float2* scratch, int ntr, int per, int ny,
