@@ -268,7 +268,7 @@ def main() -> None:
             "clocks": sampler.summary(),
             "stage_ms": stages,
             "roofline": {"bound": "hbm", "kernel": "fused spectral multiply + inverse FFT + |.| + max "
-                                                   "(k_corr_rows + k_corr_cols)",
+                                                   "(k_corr_rows + k_corr_cols2)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_BYTES_PER_STEP, "algorithmic_bytes_per_step": int(alg_bytes),
                          "peak_source": peak_src,
