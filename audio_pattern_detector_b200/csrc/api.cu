@@ -249,6 +249,11 @@ struct apd_ctx {
     void* d_unit_desc2 = nullptr;
     cudaStream_t side = nullptr;          // phase 2
     cudaStream_t pre = nullptr;           // loudness of the next sub-batch (latency-bound, hidden under phase 1)
+    cudaStream_t corr2 = nullptr;         // odd correlate launches: the row pass (HBM-bound) of one launch overlaps the
+                                          // column pass (latency-bound) of the previous one
+    cudaEvent_t corr_fork = nullptr, corr_join = nullptr;
+    float2* d_scratch_b = nullptr;        // second four-step intermediate / descriptor set for that stream
+    void* d_unit_desc_b = nullptr;
     cudaStream_t tone = nullptr;          // deferred marker-tone verification: bandwidth-heavy f64 FFT passes, at the
                                           // caller's (low) priority so that they fill the tails of the correlate launches
     cudaEvent_t scan_start = nullptr, tone_go = nullptr, tone_done = nullptr;
@@ -645,6 +650,8 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     c->scratch_elems = std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
     CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(c->inv_units)));
+    CK(dalloc(&c->d_scratch_b, (size_t)c->inv_units * max_M));
+    CK(cudaMalloc(&c->d_unit_desc_b, corr_inv_desc_bytes(c->inv_units)));
     CK(dalloc(&c->d_scratch2, (size_t)c->n_slots * max_M));
     CK(cudaMalloc(&c->d_unit_desc2, corr_inv_desc_bytes(c->n_slots)));
     c->sel_capacity = B * n_clips;
@@ -666,6 +673,9 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&c->pre, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&c->tone, cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&c->corr2, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&c->corr_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->corr_join, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->tone_go, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->tone_done, cudaEventDisableTiming));
     }
@@ -735,6 +745,11 @@ extern "C" int apd_destroy(apd_ctx* c)
     if (c->side) cudaStreamDestroy(c->side);
     if (c->pre) cudaStreamDestroy(c->pre);
     if (c->tone) cudaStreamDestroy(c->tone);
+    if (c->corr2) cudaStreamDestroy(c->corr2);
+    if (c->corr_fork) cudaEventDestroy(c->corr_fork);
+    if (c->corr_join) cudaEventDestroy(c->corr_join);
+    cudaFree(c->d_scratch_b);
+    cudaFree(c->d_unit_desc_b);
     if (c->tone_go) cudaEventDestroy(c->tone_go);
     if (c->tone_done) cudaEventDestroy(c->tone_done);
     if (c->scan_start) cudaEventDestroy(c->scan_start);
@@ -842,18 +857,32 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
     InvOut O{c->d_unit_max, c->n_clips, nullptr, 0, c->d_self_max};
     const UnitCtx X = unit_ctx(c);
     static const bool clip_major = !(getenv("APD_B200_CHUNK_MAJOR") && atoi(getenv("APD_B200_CHUNK_MAJOR")));
+    // launches alternate between the caller's stream and a second one of the same priority (own intermediate
+    // and descriptors), so that consecutive launches overlap
+    static const bool two_streams = !(getenv("APD_B200_CORR_STREAMS") && atoi(getenv("APD_B200_CORR_STREAMS")) == 1);
+    if (two_streams) {
+        CK(cudaEventRecord(c->corr_fork, st));
+        CK(cudaStreamWaitEvent(c->corr2, c->corr_fork, 0));
+    }
+    int launch = 0;
     for (auto& sc : c->shapes) {
         const int ns = (int)sc.clips.size();
         int tc = 0, tk = 0;
         if (corr_inv_supported(sc.plan) && clip_major) corr_inv_tiling(&tc, &tk);
         // unit positions of the launch sequence (with unit tiling some positions of edge tiles are unused)
         const long long nunits = tc > 0 ? corr_inv_dense_units(ns, B) : (long long)B * ns;
-        for (long long u0 = 0; u0 < nunits; u0 += c->inv_units) {
+        for (long long u0 = 0; u0 < nunits; u0 += c->inv_units, ++launch) {
             UnitSrc U{nullptr, nullptr, sc.d_clips, ns, (int)u0, clip_major ? B : 0, tc, tk};
+            const bool odd = two_streams && (launch & 1);
             launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, (int)std::min<long long>(c->inv_units, nunits - u0),
-                           c->d_scratch, c->d_unit_desc, O, false, st);
+                           odd ? c->d_scratch_b : c->d_scratch, odd ? c->d_unit_desc_b : c->d_unit_desc, O, false,
+                           odd ? c->corr2 : st);
             c->launches += tc > 0 ? 2 : 3;
         }
+    }
+    if (two_streams) {
+        CK(cudaEventRecord(c->corr_join, c->corr2));
+        CK(cudaStreamWaitEvent(st, c->corr_join, 0));
     }
     CK(cudaGetLastError());
     return APD_OK;
