@@ -107,15 +107,21 @@ template <int R, unsigned OFF> __device__ __forceinline__ c2 row_ld(const RowAdd
 
 // One work item of the row pass: rows [tile * ROWS, (tile + 1) * ROWS) of units [u_begin, u_end); unit u writes
 // its rows to Wg + (u - u_begin) * M.  buf: ROWS * 2 * 512 complex of shared memory, 1 KB aligned.
-template <int ROWS, bool KEEP_H>
+// TMA = true (dense launches, every unit in use): the section-spectrum rows are staged by 1-D TMA bulk copies
+// (cp.async.bulk on an mbarrier per row and stage) two units ahead, instead of a one-unit register prefetch.
+// buf then holds ROWS * 4 * 512 complex: per row two exchange buffers and two staging buffers; bars: ROWS * 2.
+template <int ROWS, bool KEEP_H, bool TMA = false>
 __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ D, int u_begin, int u_end, int tile,
-                                          int M, float2* __restrict__ Wg)
+                                          int M, float2* __restrict__ Wg, unsigned long long* bars = nullptr)
 {
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
     const int c = tile * ROWS + q;
+    constexpr int RS = TMA ? 4 : 2;                        // 512-element buffers per row
     // two exchange buffers per row (pass 1 -> 2 and pass 2 -> 3): one barrier per exchange, none for reuse
-    const RowAddr<8> A(smem_addr(buf + q * (2 * kN2)), j);
+    const RowAddr<8> A(smem_addr(buf + q * (RS * kN2)), j);
     constexpr unsigned kB = kN2 * 8u;                      // byte offset of the second buffer
+    const unsigned stage0 = smem_addr(buf + q * (RS * kN2) + 2 * kN2);     // staging buffers of this row (TMA)
+    const unsigned bar0 = TMA ? smem_addr(bars + q * 2) : 0u;
     float2 tw2[8], tw3[8], fs[8];
     pass_twiddles<8, +1, 8>(j, tw2);
     pass_twiddles<8, +1, 64>(j, tw3);
@@ -129,7 +135,17 @@ __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ 
     // software pipeline: the operands of unit u + 1 are requested right after the first exchange of unit u,
     // so their latency is covered by two passes of arithmetic instead of by other warps
     UnitDesc dn = load_desc(D + u_begin);
-    if (dn.n_out >= 0) {
+    if (TMA) {
+        if (j == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar0 + 8, 1);
+            mbar_init_fence();
+            const long long rrow = (long long)c * kN2;
+            tma_load_row(stage0, dn.xs + rrow, kN2 * 8u, bar0);
+            if (u_begin + 1 < u_end) tma_load_row(stage0 + kB, load_desc(D + u_begin + 1).xs + rrow, kN2 * 8u, bar0 + 8);
+        }
+        group_sync<64>(q + 1);                             // barriers initialised before anybody waits on them
+    } else if (dn.n_out >= 0) {
         const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
 #pragma unroll
         for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
@@ -138,7 +154,14 @@ __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ 
         const UnitDesc d = dn;
         const bool more = u + 1 < u_end;
         if (more) dn = load_desc(D + u + 1);
-        if (d.n_out < 0) {
+        if (TMA) {
+            const int k = u - u_begin;
+            const unsigned sb = stage0 + (k & 1) * kB + 8u * (unsigned)j;
+            mbar_wait(bar0 + 8u * (k & 1), (unsigned)((k >> 1) & 1));
+            xn[0] = lds<0>(sb); xn[1] = lds<512>(sb); xn[2] = lds<1024>(sb); xn[3] = lds<1536>(sb);
+            xn[4] = lds<2048>(sb); xn[5] = lds<2560>(sb); xn[6] = lds<3072>(sb); xn[7] = lds<3584>(sb);
+        }
+        if (!TMA && d.n_out < 0) {
             if (more && dn.n_out >= 0) {
                 const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
 #pragma unroll
@@ -164,12 +187,17 @@ __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ 
         Dft2<8, +1>::run(v);
 #pragma unroll
         for (int r = 0; r < 8; ++r) sts(A.st1 ^ (8u * r), v[r]);
-        if (more && dn.n_out >= 0) {
+        if (!TMA && more && dn.n_out >= 0) {
             const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
 #pragma unroll
             for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
         }
         group_sync<64>(q + 1);
+        if (TMA && j == 0 && u + 2 < u_end) {
+            // every thread of the row has read this unit's staging buffer (it is behind the barrier): refill it
+            const int k = u - u_begin;
+            tma_load_row(stage0 + (k & 1) * kB, load_desc(D + u + 2).xs + (long long)c * kN2, kN2 * 8u, bar0 + 8u * (k & 1));
+        }
         APD_ROW_LOAD8(A, 0, v)
         bfly_tw<8>(v, tw2);
         Dft2<8, +1>::run(v);
@@ -192,6 +220,18 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
     __shared__ __align__(1024) c2 buf[kRowsPerCta * 2 * kN2];
     const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
     rows_item<kRowsPerCta, KEEP_H>(buf, D, by * per, min(nunits, (by + 1) * per), bx, M, W + (long long)(by * per) * M);
+}
+
+// Dense phase-1 launches: section-spectrum rows staged by TMA bulk copies (64 KB of dynamic shared memory per CTA).
+__global__ void __launch_bounds__(kRowsPerCta * 64, 3)
+k_corr_rows_tma(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+{
+    extern __shared__ __align__(1024) unsigned char rows_tma_smem[];
+    c2* buf = reinterpret_cast<c2*>(rows_tma_smem);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(buf + kRowsPerCta * 4 * kN2);
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    rows_item<kRowsPerCta, false, true>(buf, D, by * per, min(nunits, (by + 1) * per), bx, M,
+                                        W + (long long)(by * per) * M, bars);
 }
 
 // ---------------------------------------------------------------- columns
@@ -615,7 +655,19 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
     const int row_tiles = P.N1 / kRowsPerCta, col_tiles = kN2 / kTB;
     const dim3 gr = swap ? dim3(ny, row_tiles) : dim3(row_tiles, ny);
     const dim3 gc = swap ? dim3(ny, col_tiles) : dim3(col_tiles, ny);
-    if (keep_h) k_corr_rows<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
+    // opt-in: measured 3 % slower than the register prefetch (profiles/sweeps_r1.txt) -- the row pass already runs at
+    // ~70 % of the HBM copy bandwidth and the staged rows cost an extra shared-memory read per element
+    static const int rows_tma = env_int2("APD_B200_ROWS_TMA", 0);
+    if (rows_tma && !write && U.list == nullptr) {
+        // dense launch: every unit position is in use, so the staging pipeline needs no holes
+        constexpr size_t kSmem = (size_t)kRowsPerCta * 4 * kN2 * sizeof(c2) + kRowsPerCta * 2 * sizeof(unsigned long long);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_corr_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+            attr = true;
+        }
+        k_corr_rows_tma<<<gr, kRowsPerCta * 64, kSmem, st>>>(D, nunits, per, P.M, scratch, swap);
+    } else if (keep_h) k_corr_rows<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     else k_corr_rows<false><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     static const int cols2 = env_int2("APD_B200_COLS2", 1);
     if (cols2 && !write) {

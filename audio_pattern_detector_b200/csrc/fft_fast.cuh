@@ -199,6 +199,36 @@ __device__ __forceinline__ c2 ldg_stream(const c2* p)      // streamed once: do 
     return r;
 }
 
+// ---------------------------------------------------------------- TMA bulk copies (global -> shared) on an mbarrier
+// 1-D cp.async.bulk: one thread arms the mbarrier with the byte count and issues the copy; consumers spin on the
+// barrier's phase parity.  Addresses and sizes are multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()      // make the initialised barriers visible to the async proxy
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_row(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "APD_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra APD_MBAR_DONE;\n"
+        "bra APD_MBAR_WAIT;\n"
+        "APD_MBAR_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // Column-kernel exchange layout: TB adjacent columns on the lanes (q = tid % TB), butterfly j = tid / TB,
 // word(e, q) = TB * (e ^ ((e >> 3) & SW)) + q with SW = 3 (TB = 4) or 1 (TB = 8); N1 = 8 * 8 * R2.
 //   loads  e = j + T r (T = N1/8 in pass 2, 64 in pass 3): 8 TB (j ^ s) + 8 q + 8 TB T r, s = (j >> 3) & SW;

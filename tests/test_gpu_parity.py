@@ -187,3 +187,21 @@ def test_16khz_auto_chunk_many_patterns():
     missing = [(n, s0) for n, s0, _g in plants if (n, max(s0 - 1, 0)) not in found]
     assert not missing, missing
     assert sum(len(v) for v in res.peak_times.values()) <= len(plants) + 8
+
+
+def test_tma_staged_row_pass_variant_matches():
+    """The opt-in TMA bulk-copy staging of the row pass (APD_B200_ROWS_TMA=1) gives the same detections."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import os; os.environ['APD_B200_ROWS_TMA'] = '1'\n"
+        "from tests.golden_util import load_json, synthetic_inputs\n"
+        "from tests.gpu_compare import compare_with_oracle\n"
+        "run = [r for r in load_json('synthetic_runs.json') if r['case']['id'] == 's8k_c60'][0]\n"
+        "clips, audio = synthetic_inputs(run); c = run['case']\n"
+        "out = compare_with_oracle(clips, audio, c['sr'], c['spc'], c.get('height_min'), max_batch_chunks=4)\n"
+        "print('OK', out['units'], out['accepted'])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
