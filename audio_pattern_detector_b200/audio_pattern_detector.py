@@ -372,11 +372,15 @@ class AudioPatternDetector:
     # ------------------------------------------------------------------ public scanning API
     def scan_array(self, audio: "NDArray[np.float32] | Any", on_pattern_detected: Optional[PatternDetectedCallback] = None,
                    collect_trace: bool = False, chunk_range: Optional[tuple[int, int]] = None,
-                   base_sample: int = 0, total_samples: Optional[int] = None) -> ScanResult:
+                   base_sample: int = 0, total_samples: Optional[int] = None, pcm_channels: int = 1) -> ScanResult:
         """Scan a whole in-memory stream (numpy array or CUDA float32 tensor).
 
         B200-side extension of the reference API: the stream is made device resident once and
         scanned ``max_batch_chunks`` chunks per launch sequence.
+
+        ``audio`` may also be interleaved integer PCM on the host (int16 / int32 array or tensor, ``pcm_channels``
+        channels): the frames are copied as they are and widened to mono float32 on the device with the
+        reference's arithmetic (row N1).
 
         Sharded use (sharding.py): ``audio`` is a slab of a longer stream starting at stream sample
         ``base_sample`` (it must contain the look-back halo of ``chunk_range[0]``), ``chunk_range``
@@ -385,14 +389,26 @@ class AudioPatternDetector:
         torch = _torch()
         devname = f"cuda:{self._device}"
         host = None
+        pcm_width = 0                     # > 0: host holds interleaved integer PCM frames (int16 / int32)
         if isinstance(audio, np.ndarray):
-            host = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
+            if audio.dtype in (np.int16, np.int32):
+                pcm_width = audio.dtype.itemsize
+                host = torch.from_numpy(np.ascontiguousarray(audio).reshape(-1))
+            else:
+                host = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
         elif not audio.is_cuda:
-            host = audio.to(dtype=torch.float32).contiguous()
+            if audio.dtype in (torch.int16, torch.int32):
+                pcm_width = audio.element_size()
+                host = audio.contiguous().reshape(-1)
+            else:
+                host = audio.to(dtype=torch.float32).contiguous()
         if host is not None:
             # host input: copied segment by segment on a copy stream, overlapped with the scan of the
-            # previous segment (pinned host memory copies at full PCIe rate)
-            dev = torch.empty(host.numel(), dtype=torch.float32, device=devname)
+            # previous segment (pinned host memory copies at full PCIe rate); integer PCM is widened on the
+            # device (apd_pcm_to_float), so only the raw frames cross PCIe
+            if pcm_width and host.numel() % pcm_channels:
+                raise ValueError("PCM input length is not a multiple of the channel count")
+            dev = torch.empty(host.numel() // (pcm_channels if pcm_width else 1), dtype=torch.float32, device=devname)
         else:
             dev = audio.to(device=devname, dtype=torch.float32).contiguous()
         n = dev.numel()
@@ -427,12 +443,23 @@ class AudioPatternDetector:
             copy_stream = torch.cuda.Stream() if host is not None else None
             ready: list[Any] = []
 
+            raw_dev = None                               # device staging of raw PCM frames (largest segment)
+            if pcm_width:
+                longest = max(b - a for a, b in zip(bounds[:-1], bounds[1:])) if len(bounds) > 1 else 0
+                raw_dev = torch.empty(min(n, longest * C_ + self._max_halo) * pcm_channels, dtype=host.dtype,
+                                      device=devname)
+
             def enqueue_copy(upto_chunk: int) -> None:
                 nonlocal copied
                 hi = min(n, upto_chunk * C_ - base_sample)
                 if hi > copied:
                     with torch.cuda.stream(copy_stream):
-                        dev[copied:hi].copy_(host[copied:hi], non_blocking=True)
+                        if pcm_width:
+                            k = (hi - copied) * pcm_channels
+                            raw_dev[:k].copy_(host[copied * pcm_channels:hi * pcm_channels], non_blocking=True)
+                            self._pcm_to_float(raw_dev, pcm_width, pcm_channels, hi - copied, dev[copied:], copy_stream)
+                        else:
+                            dev[copied:hi].copy_(host[copied:hi], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
                     ready.append(ev)
@@ -460,6 +487,62 @@ class AudioPatternDetector:
         stamps = np.concatenate(all_ts) if all_ts else np.zeros(0, dtype=np.float64)
         return ScanResult(peak_times, events, records, stamps, [c.name for c in self.audio_clips], trace, total)
 
+    def _pcm_to_float(self, raw_dev: Any, sampwidth: int, channels: int, frames: int, out_dev: Any, stream: Any) -> None:
+        rc = _lib.lib().apd_pcm_to_float(C.c_void_p(raw_dev.data_ptr()), sampwidth, channels, frames,
+                                         C.c_void_p(out_dev.data_ptr()), C.c_void_p(stream.cuda_stream))
+        if rc != _lib.APD_OK:
+            raise ValueError(f"unsupported PCM format: {sampwidth * 8}-bit, {channels} channel(s)")
+
+    def _find_clip_in_pcm(self, src: Any, peak_times: Optional[dict[str, list[float]]],
+                          on_pattern_detected: Optional[PatternDetectedCallback]
+                          ) -> tuple[dict[str, list[float]] | None, float]:
+        """Chunk loop over a raw-PCM source: ``src.read_pcm(frames) -> bytes`` and ``src.pcm_format = (sample
+        width in bytes, channels)``.  Same batches, look-back and callback order as find_clip_in_audio."""
+        torch = _torch()
+        sampwidth, channels = src.pcm_format
+        np_dt, t_dt = (np.int16, torch.int16) if sampwidth == 2 else (np.int32, torch.int32)
+        sr, C_ = self.target_sample_rate, self._chunk_samples
+        events: list[tuple[float, str]] = []
+        total_time = 0.0
+        dev = f"cuda:{self._device}"
+        cap = self._max_halo + self._max_batch * C_
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream()
+            fbuf = torch.empty(cap, dtype=torch.float32, device=dev)
+            raw_pin = torch.empty(self._max_batch * C_ * channels, dtype=t_dt).pin_memory()
+            raw_dev = torch.empty_like(raw_pin, device=dev)
+            n_halo, chunk_index, eof = 0, 0, False
+            while not eof:
+                frames = 0
+                n_chunks = 0
+                host = raw_pin.numpy()
+                while n_chunks < self._max_batch:
+                    data = src.read_pcm(C_)
+                    if not data:
+                        eof = True
+                        break
+                    got = len(data) // (sampwidth * channels)
+                    host[frames * channels:(frames + got) * channels] = np.frombuffer(data, dtype=np_dt)
+                    total_time += got / sr                                   # reference :301
+                    frames += got
+                    n_chunks += 1
+                    if got != C_:
+                        eof = True
+                        break
+                if n_chunks == 0:
+                    break
+                raw_dev[:frames * channels].copy_(raw_pin[:frames * channels], non_blocking=True)
+                self._pcm_to_float(raw_dev, sampwidth, channels, frames, fbuf[n_halo:], stream)
+                n_tot = n_halo + frames
+                c0, c1 = chunk_index, chunk_index + n_chunks
+                rec, _ = self._scan_batch(fbuf.data_ptr(), c0 * C_ - n_halo, n_tot, c0, c1, False)
+                self._emit_batch(rec, self._timestamps(rec), peak_times, events, on_pattern_detected)
+                keep = min(self._max_halo, n_tot)
+                fbuf[:keep] = fbuf[n_tot - keep:n_tot].clone()               # look-back stays on the device
+                n_halo = keep
+                chunk_index = c1
+        return peak_times, total_time
+
     def find_clip_in_audio(self, audio_stream: AudioStream,
                            on_pattern_detected: PatternDetectedCallback | None = None,
                            accumulate_results: bool = True) -> tuple[dict[str, list[float]] | None, float]:
@@ -477,6 +560,10 @@ class AudioPatternDetector:
         events: list[tuple[float, str]] = []
         total_time = 0.0
         src = audio_stream.audio_stream
+        if getattr(src, "pcm_format", None) is not None:
+            # raw integer PCM at the detector's rate (e.g. match._WavFileStreamWrapper on a 16/32-bit WAV): the
+            # frames cross PCIe as they are and are widened on the device (row N1, apd_pcm_to_float)
+            return self._find_clip_in_pcm(src, peak_times, on_pattern_detected)
         halo = np.zeros(0, dtype=np.float32)          # tail of the previous batch (look-back)
         chunk_index = 0
         eof = False

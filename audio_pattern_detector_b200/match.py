@@ -153,6 +153,10 @@ class _WavFileStreamWrapper:
         self._channels = self._wav.getnchannels()
         self._sampwidth = self._wav.getsampwidth()
         self.needs_resample = self.input_sample_rate != target_sample_rate
+        # raw frames can go to the device as they are when no resampling is needed and the samples are 16/32-bit
+        # integers; the detector then widens them there (AudioPatternDetector._find_clip_in_pcm)
+        self.pcm_format = ((self._sampwidth, self._channels)
+                           if not self.needs_resample and self._sampwidth in (2, 4) and self._channels <= 8 else None)
         if self._channels != 1:
             print(f"Warning: WAV has {self._channels} channels, will be mixed to mono", file=sys.stderr)
 
@@ -186,6 +190,15 @@ class _WavFileStreamWrapper:
         if self.needs_resample:
             audio = resample_audio(audio, self.input_sample_rate, self.target_sample_rate)
         return audio.tobytes()
+
+    def read_pcm(self, frames: int, /) -> bytes:
+        """Raw interleaved PCM frames (only meaningful when ``pcm_format`` is set)."""
+        raw = self._wav.readframes(frames)
+        if raw and not self._validated:
+            self._validated = True
+            if not any(raw):
+                print("Warning: First chunk is all zeros - verify input is correct", file=sys.stderr)
+        return raw
 
     def close(self) -> None:
         self._wav.close()

@@ -239,6 +239,14 @@ def main() -> None:
     ms_e2e, res_h = timed(through_host, max(1, min(args.steps, 2)))
     assert res_h.peak_times == res.peak_times
 
+    # row N1 (streaming ingestion): the same scan from 16-bit PCM in pinned host memory -- half the PCIe bytes, widened
+    # to float32 on the device (apd_pcm_to_float); the stream is the synthetic one quantised to int16
+    pcm = (audio * 32768.0).round_().clamp_(-32768, 32767).to(torch.int16).cpu().pin_memory()
+    through_pcm = lambda: det.scan_array(pcm)           # noqa: E731
+    through_pcm()
+    ms_pcm, res_p = timed(through_pcm, max(1, min(args.steps, 2)))
+    del pcm
+
     # the dominant stage timed alone (nothing else on the GPU), for the roofline of the kernel itself; the
     # in-step figure above shares the SMs with the overlapped phase-2 and loudness streams
     iso_ms, iso_launches = det.time_correlate_stage(audio)
@@ -264,6 +272,9 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 4),
                     "d2h_bytes_per_step": int(res.n_candidates * 176 + n_chunks // args.batch_chunks * 64),
                     "ms_per_step": ms_e2e},
+            "e2e_pcm16": {"value": hours_total / (ms_pcm / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(n * 2),
+                          "ms_per_step": ms_pcm, "detections_per_step": sum(len(v) for v in res_p.peak_times.values()),
+                          "note": "same scan from int16 PCM in pinned host memory, widened on the device (row N1)"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "stage_ms": stages,

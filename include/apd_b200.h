@@ -143,6 +143,13 @@ APD_API int apd_stage_unit_correlation(apd_ctx* ctx, int32_t chunk, int32_t clip
 APD_API int apd_profile(apd_ctx* ctx, int enable);
 APD_API int apd_profile_read(apd_ctx* ctx, double* ms4, int reset);
 
+/* Streaming ingestion (row N1): integer PCM frames, already on the device, to mono float32 with the reference's
+ * arithmetic (_WavFileStreamWrapper.read / _normalize_wav_data, match.py:393-427, audio_utils.py:60-79,132-151):
+ * int16 / 32768 or int32 / 2^31, channels averaged in float32.  sample_width_bytes is 2 or 4, channels 1..8.
+ * Needs no context; returns APD_ERR_* without setting apd_last_error(). */
+APD_API int apd_pcm_to_float(const void* pcm_dev, int sample_width_bytes, int channels, int64_t n_frames,
+                     float* out_dev, void* cuda_stream);
+
 /* Introspection for the bench: algorithmic byte counts and kernel launch counter. */
 APD_API int64_t apd_launch_count(apd_ctx* ctx);
 APD_API int apd_unit_n_out(apd_ctx* ctx, int32_t chunk, int32_t clip, int64_t total_samples, int32_t* n_out);
