@@ -568,7 +568,10 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         for (int k = 0; k < 6; ++k) h_thr[p * 6 + k] = given[k] == given[k] ? given[k] : defaults[k];
         if (cl.strategy == APD_STRATEGY_MARKER_TONE && cl.tone_hz > 0.0) {
             int P = 2;
-            while (P < 2 * L - 1) P <<= 1;
+            // chirp-z over the K = L/2 + 1 bins the metrics use (not all L): the circular convolution only has to
+            // hold indices k - n in (-L, K), so P >= L + K - 1 suffices (half the 2L - 1 of a full Bluestein DFT
+            // for about half of all clip lengths)
+            while (P < L + (L / 2 + 1) - 1) P <<= 1;
             cl.tone_P = P;
             max_P = std::max(max_P, P);
             std::vector<double2> tw(P / 2);

@@ -251,7 +251,7 @@ __device__ __forceinline__ double2 chirp(long long n, int L, double sign)   // e
     return make_double2(c, s);
 }
 
-// Init-time tables of one tone clip: FFT_P of the wrapped chirp b[m] = e^{+i pi m^2 / L} (|m| < L),
+// Init-time tables of one tone clip: FFT_P of the wrapped chirp b[m] = e^{+i pi m^2 / L} (-L < m <= L/2),
 // pre[n] = hann_L[n] * e^{-i pi n^2 / L} and post[k] = e^{-i pi k^2 / L} (k <= L/2).
 __global__ void __launch_bounds__(1024)
 k_tone_tables(int L, int P, const double2* __restrict__ tw, double2* buf0, double2* buf1, double2* chirp_fft,
@@ -259,8 +259,8 @@ k_tone_tables(int L, int P, const double2* __restrict__ tw, double2* buf0, doubl
 {
     for (int m = threadIdx.x; m < P; m += blockDim.x) {
         double2 v = make_double2(0, 0);
-        if (m < L) v = chirp(m, L, +1.0);
-        else if (P - m < L) v = chirp(P - m, L, +1.0);
+        if (m <= L / 2) v = chirp(m, L, +1.0);                     // b[m], m in [0, K), K = L/2 + 1 output bins
+        else if (P - m < L) v = chirp(P - m, L, +1.0);             // b[-m'], m' in [1, L)
         buf0[m] = v;
     }
     for (int n = threadIdx.x; n < L; n += blockDim.x) {
