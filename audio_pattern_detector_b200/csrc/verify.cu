@@ -475,11 +475,14 @@ k_tone_stats(VerifyArgs A, ToneRound T)
     }
 }
 
-// STFT frame bins (du.py:77-100): thread = (frame, bin) of one (item, segment); |X|^2 into buffer B.
+// STFT frame bins (du.py:77-100): a CTA owns kFramesPerCta consecutive frames of one (item, segment), stages their
+// windowed samples once in shared memory, then thread = (frame, bin) accumulates its DFT bin; |X|^2 into buffer B.
+constexpr int kFramesPerCta = 2;
+
 __global__ void __launch_bounds__(256)
 k_tone_frames(VerifyArgs A, ToneRound T)
 {
-    extern __shared__ double2 ftw[];            // e^{-2 pi i t / wl} (t < wl), then the frame Hann window (.x)
+    extern __shared__ double2 ftw[];            // e^{-2 pi i t / wl} (t < wl), the frame Hann window (.x), then samples
     const int r = blockIdx.z, seg = blockIdx.y;
     if (r >= T.n_round) return;
     if (T.stats[((long long)r * 3 + seg) * 4] == 0.0) return;                 // du.py:65-72
@@ -487,8 +490,9 @@ k_tone_frames(VerifyArgs A, ToneRound T)
     const int wl = T.wl, hop = T.hop;
     const int nf = s.L - wl > 0 ? (s.L - wl + hop - 1) / hop : 0;             // range(0, L - wl, hop)
     const int nbw = wl / 2 + 1;
-    const long long work = (long long)nf * nbw;
-    if ((long long)blockIdx.x * blockDim.x >= work) return;
+    const int f0 = blockIdx.x * kFramesPerCta;
+    if (f0 >= nf) return;
+    double* xw = reinterpret_cast<double*>(ftw + 2 * wl);                     // [kFramesPerCta][wl]
     for (int t = threadIdx.x; t < wl; t += blockDim.x) {
         double sn, cs;
         sincospi(-2.0 * (double)t / (double)wl, &sn, &cs);
@@ -496,20 +500,25 @@ k_tone_frames(VerifyArgs A, ToneRound T)
         ftw[wl + t] = make_double2(wl > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(wl - 1)) : 1.0, 0.0);
     }
     __syncthreads();
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(w / nbw), kb = (int)(w % nbw);
-        const int s0 = s.ms + f * hop;
+    for (int t = threadIdx.x; t < kFramesPerCta * wl; t += blockDim.x) {
+        const int fl = t / wl, n = t - fl * wl;
+        if (f0 + fl < nf) xw[t] = tone_sample(s, s.ms + (f0 + fl) * hop + n) * ftw[wl + n].x;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kFramesPerCta * nbw; t += blockDim.x) {
+        const int fl = t / nbw, kb = t - fl * nbw;
+        if (f0 + fl >= nf) continue;
+        const double* __restrict__ x = xw + fl * wl;
         double re = 0, im = 0;
         int ph = 0;
         for (int n = 0; n < wl; ++n) {
-            const double xw = tone_sample(s, s0 + n) * ftw[wl + n].x;
             const double2 e = ftw[ph];
-            re += xw * e.x;
-            im += xw * e.y;
+            re += x[n] * e.x;
+            im += x[n] * e.y;
             ph += kb;
             if (ph >= wl) ph -= wl;
         }
-        ((double*)tone_buf(T, r, seg, 1))[w] = re * re + im * im;
+        ((double*)tone_buf(T, r, seg, 1))[(long long)(f0 + fl) * nbw + kb] = re * re + im * im;
     }
 }
 
@@ -710,7 +719,8 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
             k_tone_fft_pass<true><<<dim3(gx, 3, R), 256, 0, st>>>(A, T, s);
         k_tone_stats<<<dim3(3, R), 1024, 0, st>>>(A, T);
         if (work_max > 0) {
-            k_tone_frames<<<dim3((unsigned)((work_max + 255) / 256), 3, R), 256, (size_t)2 * wl * sizeof(double2), st>>>(A, T);
+            k_tone_frames<<<dim3((unsigned)((nf_max + kFramesPerCta - 1) / kFramesPerCta), 3, R), 256,
+                            (size_t)2 * wl * sizeof(double2) + (size_t)kFramesPerCta * wl * sizeof(double), st>>>(A, T);
             k_tone_frame_stats<<<dim3((nf_max + 127) / 128, 3, R), 128, 0, st>>>(A, T);
         }
         k_tone_final<<<(T.n_round * 3 + 63) / 64, 64, 0, st>>>(A, T);
