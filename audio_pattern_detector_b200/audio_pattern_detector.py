@@ -349,11 +349,57 @@ class AudioPatternDetector:
                         "n_peaks": u.n_peaks, "lufs": lufs[ci * ncl + p]}
         return rec, tr
 
+    def _dump_debug(self, rec: "NDArray[Any]") -> None:
+        """``--debug`` score dump (row N4; reference :563-582, :793-804, :880-895): per (chunk, clip) with peaks,
+        ``{debug_dir}/debug/cross_correlation_{clip}/{index}_{section_ts}.txt`` holding the find_peaks result, the
+        seconds of the verified candidates and their similarity / Pearson scores.  (The reference's PNG graphs and
+        WAV excerpts are debug tooling outside the hot path and are not produced.)"""
+        import json
+        from .audio_utils import seconds_to_time
+        sr = self.target_sample_rate
+        names = [c.name for c in self.audio_clips]
+        keys = np.stack([rec["chunk"], rec["clip"]], axis=1) if rec.size else np.zeros((0, 2), dtype=np.int32)
+        start = 0
+        while start < rec.shape[0]:
+            end = start
+            while end < rec.shape[0] and (keys[end] == keys[start]).all():
+                end += 1
+            index, clip = int(keys[start][0]), int(keys[start][1])
+            peaks, seconds, similarities = [], [], []
+            for r in rec[start:end]:
+                flags = int(r["flags"])
+                kind = (flags >> _lib.KIND_SHIFT) & 3
+                peaks.append(int(r["peak"]))
+                if kind == 2 or flags & _lib.FLAG_SKIPPED:            # tone clips / bounds gate: no similarity entry
+                    continue
+                seconds.append(int(r["peak"]) / sr)
+                whole, middle = float(r["similarity_whole"]), float(r["similarity_middle"])
+                sim = whole if kind == 1 else min(whole, middle)
+                parts = {"whole": whole, "middle": middle}
+                pr = [float(v) for v in r["pearson"]]
+                if np.isnan(pr[0]):                                    # rejected on similarity before Pearson
+                    similarities.append((sim, parts, None))
+                    continue
+                wins = [(0, 10)] if kind == 1 else [(0, 5), (4, 6), (5, 10)]
+                best = max(range(len(wins)), key=lambda i: (pr[i], -i))
+                d = {"pearson_r": pr[0 if kind == 1 else 1], "best_window_left": float(wins[best][0]),
+                     "best_window_right": float(wins[best][1])}
+                d.update({f"pearson_w{a}_{b}": pr[i] for i, (a, b) in enumerate(wins)})
+                similarities.append((sim, parts, d))
+            section_ts = seconds_to_time(seconds=index * self.seconds_per_chunk, include_decimals=False)
+            out_dir = f"{self.debug_dir}/debug/cross_correlation_{names[clip]}"
+            os.makedirs(out_dir, exist_ok=True)
+            with open(f"{out_dir}/{index}_{section_ts}.txt", "w") as f:
+                print(json.dumps({"peaks": peaks, "seconds": seconds, "similarities": similarities}, indent=2), file=f)
+            start = end
+
     def _emit_batch(self, rec: "NDArray[Any]", ts: "NDArray[np.float64]",
                     peak_times: Optional[dict[str, list[float]]], events: list[tuple[float, str]],
                     on_pattern_detected: Optional[PatternDetectedCallback]) -> None:
         """Accepted candidates -> results, in the reference's order (:303-327): per chunk the clips in list
         order (the table is ordered by chunk, clip, peak), then a stable sort by timestamp inside the chunk."""
+        if self.debug_mode:
+            self._dump_debug(rec)
         acc = np.flatnonzero(rec["flags"] & _lib.FLAG_ACCEPT)
         if acc.size == 0:
             return

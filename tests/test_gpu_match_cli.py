@@ -78,3 +78,27 @@ def test_cli_jsonl_contract(files):
     assert det["clip_name"] == "cbs_news" and det["timestamp_ms"] == round(25.89875 * 1000)
     assert isinstance(det["timestamp_formatted"], str)
     assert events[2]["total_time_ms"] == round(RUNS["cbs_news_audio_section.wav"]["total_time"] * 1000)
+
+
+def test_debug_score_dump(files, tmp_path):
+    """--debug writes the reference's per-(chunk, clip) score dump (apd.py:574-580); values against the trace the
+    unmodified reference produced on the same fixture."""
+    from audio_pattern_detector_b200.match import match_pattern
+    patterns = sorted(os.path.join(files["clips"], f) for f in os.listdir(files["clips"]))
+    dbg = tmp_path / "dbg"
+    match_pattern(files["cbs_news_audio_section.wav"], patterns, debug_mode=True, debug_dir=str(dbg))
+    path = dbg / "debug" / "cross_correlation_cbs_news" / "0_00:00:00.txt"
+    assert path.exists()
+    dump = json.loads(path.read_text())
+    ref = [u for u in RUNS["cbs_news_audio_section.wav"]["units"] if u["clip"] == "cbs_news" and u["peaks"]][0]
+    cand = ref["cands"][0]
+    assert dump["peaks"] == ref["peaks"] and dump["seconds"] == [ref["peaks"][0] / 8000]
+    sim, parts, pearson = dump["similarities"][0]
+    assert abs(parts["whole"] - cand["similarity_whole"]) <= 1e-4 * cand["similarity_whole"]
+    assert abs(parts["middle"] - cand["similarity_middle"]) <= 1e-4 * cand["similarity_middle"]
+    assert sim == min(parts["whole"], parts["middle"])
+    assert abs(pearson["pearson_r"] - cand["pearson"][1]) < 1e-4 and pearson["pearson_r"] == pearson["pearson_w4_6"]
+    assert (pearson["best_window_left"], pearson["best_window_right"]) == (4.0, 6.0)
+    assert set(pearson) == {"pearson_r", "best_window_left", "best_window_right", "pearson_w0_5", "pearson_w4_6",
+                            "pearson_w5_10"}
+    assert not (dbg / "debug" / "cross_correlation_天空下的彩虹intro").exists()      # no peaks -> no file
