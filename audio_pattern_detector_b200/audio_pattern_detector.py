@@ -128,7 +128,7 @@ class AudioPatternDetector:
                  seconds_per_chunk: int | None = DEFAULT_SECONDS_PER_CHUNK,
                  target_sample_rate: int | None = None, debug_dir: str = "./tmp",
                  height_min: float | None = None, *, device: int | None = None,
-                 max_batch_chunks: int | None = None) -> None:
+                 max_batch_chunks: int | None = None, stream_read_chunks: int | None = None) -> None:
         self.audio_clips = audio_clips
         self.debug_mode = debug_mode
         self.debug_dir = debug_dir
@@ -184,6 +184,9 @@ class AudioPatternDetector:
         torch = _torch()
         self._device = torch.cuda.current_device() if device is None else int(device)
         self._max_batch = int(max_batch_chunks or os.environ.get("APD_B200_BATCH_CHUNKS", DEFAULT_BATCH_CHUNKS))
+        # find_clip_in_audio reads this many chunks per device scan: several sub-batches, so that apd_scan can overlap
+        # its phases; a caller that wants the reference's per-chunk callback latency on a live stream passes 1
+        self._stream_read_chunks = int(stream_read_chunks) if stream_read_chunks else 4 * self._max_batch
         descs = (_lib.ClipDesc * len(audio_clips))()
         self._keepalive: list[NDArray[np.float32]] = []
         nan = float("nan")
@@ -551,18 +554,18 @@ class AudioPatternDetector:
         events: list[tuple[float, str]] = []
         total_time = 0.0
         dev = f"cuda:{self._device}"
-        cap = self._max_halo + self._max_batch * C_
+        cap = self._max_halo + self._stream_read_chunks * C_
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream()
             fbuf = torch.empty(cap, dtype=torch.float32, device=dev)
-            raw_pin = torch.empty(self._max_batch * C_ * channels, dtype=t_dt).pin_memory()
+            raw_pin = torch.empty(self._stream_read_chunks * C_ * channels, dtype=t_dt).pin_memory()
             raw_dev = torch.empty_like(raw_pin, device=dev)
             n_halo, chunk_index, eof = 0, 0, False
             while not eof:
                 frames = 0
                 n_chunks = 0
                 host = raw_pin.numpy()
-                while n_chunks < self._max_batch:
+                while n_chunks < self._stream_read_chunks:
                     data = src.read_pcm(C_)
                     if not data:
                         eof = True
@@ -613,14 +616,14 @@ class AudioPatternDetector:
         halo = np.zeros(0, dtype=np.float32)          # tail of the previous batch (look-back)
         chunk_index = 0
         eof = False
-        cap = self._max_halo + self._max_batch * C_
+        cap = self._max_halo + self._stream_read_chunks * C_
         with torch.cuda.device(self._device):
             if self._dev_buf is None:
                 self._dev_buf = torch.empty(cap, dtype=torch.float32, device=f"cuda:{self._device}")
                 self._pinned = torch.empty(cap, dtype=torch.float32).pin_memory()
             while not eof:
                 parts: list[NDArray[np.float32]] = []
-                while len(parts) < self._max_batch:
+                while len(parts) < self._stream_read_chunks:
                     data = src.read(self._chunk_size)
                     if not data:
                         eof = True

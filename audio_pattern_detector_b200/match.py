@@ -206,10 +206,13 @@ class _WavFileStreamWrapper:
 
 def _detect(stream: Any, name: str, clips: list[AudioClip], sr: int, *, debug_mode: bool,
             on_pattern_detected: PatternDetectedCallback | None, accumulate_results: bool,
-            seconds_per_chunk: int | None, debug_dir: str, height_min: float | None
+            seconds_per_chunk: int | None, debug_dir: str, height_min: float | None, live: bool = False
             ) -> tuple[dict[str, list[float]] | None, float]:
+    # a pipe may be a live stream: scan chunk by chunk there, so detections are reported as the reference reports
+    # them (after every chunk read); a file is scanned many chunks per device call
     detector = AudioPatternDetector(debug_mode=debug_mode, audio_clips=clips, seconds_per_chunk=seconds_per_chunk,
-                                    target_sample_rate=sr, debug_dir=debug_dir, height_min=height_min)
+                                    target_sample_rate=sr, debug_dir=debug_dir, height_min=height_min,
+                                    max_batch_chunks=1 if live else None, stream_read_chunks=1 if live else None)
     return detector.find_clip_in_audio(AudioStream(name=name, audio_stream=stream, sample_rate=sr),
                                        on_pattern_detected=on_pattern_detected,
                                        accumulate_results=accumulate_results)
@@ -242,7 +245,7 @@ def match_pattern(audio_source: str | None, pattern_files: list[str], debug_mode
     if from_stdin:
         wrapper = _WavStdinStreamWrapper(sr)
         print("Finding pattern in audio stream stdin...", file=sys.stderr)
-        return _detect(wrapper, "stdin", clips, sr, height_min=height_min, **common)
+        return _detect(wrapper, "stdin", clips, sr, height_min=height_min, live=True, **common)
     assert audio_source is not None
     name = Path(audio_source).stem
     print(f"Finding pattern in audio file {name}...", file=sys.stderr)
@@ -254,7 +257,7 @@ def match_pattern(audio_source: str | None, pattern_files: list[str], debug_mode
             wrapper2.close()
     with ffmpeg_get_float32_pcm(audio_source, target_sample_rate=sr, ac=1) as pipe:
         # the reference does not forward height_min on this branch (match.py:199-205); kept as is
-        return _detect(pipe, name, clips, sr, height_min=None, **common)
+        return _detect(pipe, name, clips, sr, height_min=None, live=True, **common)
 
 
 def _match_pattern_multiplexed_stdin(debug_mode: bool, on_pattern_detected: PatternDetectedCallback | None,
@@ -268,7 +271,7 @@ def _match_pattern_multiplexed_stdin(debug_mode: bool, on_pattern_detected: Patt
     wrapper = _WavStdinStreamWrapper(target_sample_rate)
     return _detect(wrapper, "stdin", clips, target_sample_rate, debug_mode=debug_mode,
                    on_pattern_detected=on_pattern_detected, accumulate_results=accumulate_results,
-                   seconds_per_chunk=seconds_per_chunk, debug_dir=debug_dir, height_min=height_min)
+                   seconds_per_chunk=seconds_per_chunk, debug_dir=debug_dir, height_min=height_min, live=True)
 
 
 def _make_jsonl_callback(timestamp_format: str = "both") -> PatternDetectedCallback:
