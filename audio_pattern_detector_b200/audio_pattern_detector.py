@@ -555,32 +555,41 @@ class AudioPatternDetector:
         total_time = 0.0
         dev = f"cuda:{self._device}"
         cap = self._max_halo + self._stream_read_chunks * C_
-        with torch.cuda.device(self._device):
+        from concurrent.futures import ThreadPoolExecutor
+        per_read = self._stream_read_chunks
+        with torch.cuda.device(self._device), ThreadPoolExecutor(1) as pool:
             stream = torch.cuda.current_stream()
             fbuf = torch.empty(cap, dtype=torch.float32, device=dev)
-            raw_pin = torch.empty(self._stream_read_chunks * C_ * channels, dtype=t_dt).pin_memory()
-            raw_dev = torch.empty_like(raw_pin, device=dev)
-            n_halo, chunk_index, eof = 0, 0, False
-            while not eof:
-                frames = 0
-                n_chunks = 0
-                host = raw_pin.numpy()
-                while n_chunks < self._stream_read_chunks:
-                    data = src.read_pcm(C_)
-                    if not data:
-                        eof = True
-                        break
-                    got = len(data) // (sampwidth * channels)
-                    host[frames * channels:(frames + got) * channels] = np.frombuffer(data, dtype=np_dt)
-                    total_time += got / sr                                   # reference :301
-                    frames += got
-                    n_chunks += 1
-                    if got != C_:
-                        eof = True
-                        break
-                if n_chunks == 0:
+            pins = [torch.empty(per_read * C_ * channels, dtype=t_dt).pin_memory() for _ in range(2)]
+            raw_dev = torch.empty_like(pins[0], device=dev)
+
+            def read_batch(which: int) -> int:
+                """One large read of up to per_read chunks into pinned buffer `which`; returns the frames read.
+                Runs on the reader thread, overlapped with the device scan of the previous batch (apd_scan
+                releases the GIL)."""
+                if hasattr(src, "readinto_pcm"):                              # straight into pinned memory
+                    return src.readinto_pcm(pins[which].numpy(), per_read * C_)
+                data = src.read_pcm(per_read * C_)
+                got = len(data) // (sampwidth * channels)
+                if got:
+                    pins[which].numpy()[:got * channels] = np.frombuffer(data, dtype=np_dt, count=got * channels)
+                return got
+
+            n_halo, chunk_index, which = 0, 0, 0
+            pending = pool.submit(read_batch, which)
+            while True:
+                frames = pending.result()
+                if frames == 0:
                     break
-                raw_dev[:frames * channels].copy_(raw_pin[:frames * channels], non_blocking=True)
+                last = frames < per_read * C_                                # a short read ends the stream
+                cur = which
+                if not last:
+                    which ^= 1
+                    pending = pool.submit(read_batch, which)                 # next batch while this one is scanned
+                n_chunks = (frames + C_ - 1) // C_
+                for k in range(n_chunks):                                    # reference :301, chunk by chunk
+                    total_time += (min((k + 1) * C_, frames) - k * C_) / sr
+                raw_dev[:frames * channels].copy_(pins[cur][:frames * channels], non_blocking=True)
                 self._pcm_to_float(raw_dev, sampwidth, channels, frames, fbuf[n_halo:], stream)
                 n_tot = n_halo + frames
                 c0, c1 = chunk_index, chunk_index + n_chunks
@@ -590,6 +599,8 @@ class AudioPatternDetector:
                 fbuf[:keep] = fbuf[n_tot - keep:n_tot].clone()               # look-back stays on the device
                 n_halo = keep
                 chunk_index = c1
+                if last:
+                    break
         return peak_times, total_time
 
     def find_clip_in_audio(self, audio_stream: AudioStream,

@@ -153,6 +153,8 @@ class _WavFileStreamWrapper:
         self._channels = self._wav.getnchannels()
         self._sampwidth = self._wav.getsampwidth()
         self.needs_resample = self.input_sample_rate != target_sample_rate
+        self._raw: Any = None
+        self._raw_left = 0
         # raw frames can go to the device as they are when no resampling is needed and the samples are 16/32-bit
         # integers; the detector then widens them there (AudioPatternDetector._find_clip_in_pcm)
         self.pcm_format = ((self._sampwidth, self._channels)
@@ -191,6 +193,43 @@ class _WavFileStreamWrapper:
             audio = resample_audio(audio, self.input_sample_rate, self.target_sample_rate)
         return audio.tobytes()
 
+    def readinto_pcm(self, buf: Any, frames: int, /) -> int:
+        """Read up to ``frames`` raw PCM frames straight into ``buf`` (a writable byte buffer, e.g. pinned host
+        memory) without intermediate bytes objects; returns the frames read.  Uses its own handle on the file's
+        ``data`` chunk, found by walking the RIFF chunks."""
+        if self._raw is None:
+            f = open(self._file_path, "rb")
+            head = f.read(12)
+            if head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+                f.close()
+                raise ValueError(f"Not a WAV file: {self._file_path}")
+            while True:
+                hdr = f.read(8)
+                if len(hdr) < 8:
+                    f.close()
+                    raise ValueError(f"WAV file {self._file_path} has no data chunk")
+                size = struct.unpack("<I", hdr[4:])[0]
+                if hdr[:4] == b"data":
+                    self._raw, self._raw_left = f, min(size, self._wav.getnframes() * self._sampwidth * self._channels)
+                    break
+                f.seek(size + (size & 1), 1)
+        frame_bytes = self._sampwidth * self._channels
+        want = min(frames * frame_bytes, self._raw_left)
+        view = memoryview(buf).cast("B")[:want]
+        got = 0
+        while got < want:
+            k = self._raw.readinto(view[got:])
+            if not k:
+                break
+            got += k
+        got -= got % frame_bytes
+        self._raw_left -= got
+        if got and not self._validated:
+            self._validated = True
+            if not any(view[:min(got, 1 << 20)]):
+                print("Warning: First chunk is all zeros - verify input is correct", file=sys.stderr)
+        return got // frame_bytes
+
     def read_pcm(self, frames: int, /) -> bytes:
         """Raw interleaved PCM frames (only meaningful when ``pcm_format`` is set)."""
         raw = self._wav.readframes(frames)
@@ -202,6 +241,9 @@ class _WavFileStreamWrapper:
 
     def close(self) -> None:
         self._wav.close()
+        if self._raw is not None:
+            self._raw.close()
+            self._raw = None
 
 
 def _detect(stream: Any, name: str, clips: list[AudioClip], sr: int, *, debug_mode: bool,
