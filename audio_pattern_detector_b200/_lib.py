@@ -59,6 +59,9 @@ PROTOTYPES: dict[str, tuple[Any, list[Any]]] = {
     "apd_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "apd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "apd_pcm_to_float": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "apd_resample_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
+    "apd_resample": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                               C.c_void_p, C.c_int64, C.c_void_p]),
     "apd_launch_count": (C.c_int64, [C.c_void_p]),
     "apd_unit_n_out": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int32)]),
 }

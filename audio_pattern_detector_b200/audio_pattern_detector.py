@@ -546,11 +546,21 @@ class AudioPatternDetector:
                           on_pattern_detected: Optional[PatternDetectedCallback]
                           ) -> tuple[dict[str, list[float]] | None, float]:
         """Chunk loop over a raw-PCM source: ``src.read_pcm(frames) -> bytes`` and ``src.pcm_format = (sample
-        width in bytes, channels)``.  Same batches, look-back and callback order as find_clip_in_audio."""
+        width in bytes, channels)``.  Same batches, look-back and callback order as find_clip_in_audio.
+
+        ``src.pcm_sample_rate`` (optional) is the rate of the frames when it differs from the detector's: every
+        chunk read is then resampled on its own, on the device, exactly as the reference resamples what each
+        ``read`` returns (match.py:395-423: ``int(chunk * in_rate / rate)`` frames in, ``int(len * rate / in_rate)``
+        samples out, row N2)."""
         torch = _torch()
         sampwidth, channels = src.pcm_format
         np_dt, t_dt = (np.int16, torch.int16) if sampwidth == 2 else (np.int32, torch.int32)
         sr, C_ = self.target_sample_rate, self._chunk_samples
+        in_sr = int(getattr(src, "pcm_sample_rate", None) or sr)
+        resampling = in_sr != sr
+        Cin = int(C_ * in_sr / sr) if resampling else C_                      # frames per chunk read, match.py:398
+        if resampling and (Cin < 1 or int(Cin * sr / in_sr) != C_):
+            raise ValueError(f"cannot cut a {in_sr} Hz source into chunks of {C_} samples at {sr} Hz")
         events: list[tuple[float, str]] = []
         total_time = 0.0
         dev = f"cuda:{self._device}"
@@ -560,7 +570,8 @@ class AudioPatternDetector:
         with torch.cuda.device(self._device), ThreadPoolExecutor(1) as pool:
             stream = torch.cuda.current_stream()
             fbuf = torch.empty(cap, dtype=torch.float32, device=dev)
-            pins = [torch.empty(per_read * C_ * channels, dtype=t_dt).pin_memory() for _ in range(2)]
+            fin = torch.empty(per_read * Cin, dtype=torch.float32, device=dev) if resampling else None
+            pins = [torch.empty(per_read * Cin * channels, dtype=t_dt).pin_memory() for _ in range(2)]
             raw_dev = torch.empty_like(pins[0], device=dev)
 
             def read_batch(which: int) -> int:
@@ -568,8 +579,8 @@ class AudioPatternDetector:
                 Runs on the reader thread, overlapped with the device scan of the previous batch (apd_scan
                 releases the GIL)."""
                 if hasattr(src, "readinto_pcm"):                              # straight into pinned memory
-                    return src.readinto_pcm(pins[which].numpy(), per_read * C_)
-                data = src.read_pcm(per_read * C_)
+                    return src.readinto_pcm(pins[which].numpy(), per_read * Cin)
+                data = src.read_pcm(per_read * Cin)
                 got = len(data) // (sampwidth * channels)
                 if got:
                     pins[which].numpy()[:got * channels] = np.frombuffer(data, dtype=np_dt, count=got * channels)
@@ -581,17 +592,31 @@ class AudioPatternDetector:
                 frames = pending.result()
                 if frames == 0:
                     break
-                last = frames < per_read * C_                                # a short read ends the stream
+                last = frames < per_read * Cin                               # a short read ends the stream
                 cur = which
                 if not last:
                     which ^= 1
                     pending = pool.submit(read_batch, which)                 # next batch while this one is scanned
-                n_chunks = (frames + C_ - 1) // C_
-                for k in range(n_chunks):                                    # reference :301, chunk by chunk
-                    total_time += (min((k + 1) * C_, frames) - k * C_) / sr
                 raw_dev[:frames * channels].copy_(pins[cur][:frames * channels], non_blocking=True)
-                self._pcm_to_float(raw_dev, sampwidth, channels, frames, fbuf[n_halo:], stream)
-                n_tot = n_halo + frames
+                if resampling:
+                    from .resample import resample_into
+                    self._pcm_to_float(raw_dev, sampwidth, channels, frames, fin, stream)
+                    full, rem = divmod(frames, Cin)
+                    tail = int(rem * sr / in_sr)                             # audio_utils.py:170
+                    if full:
+                        resample_into(fin, Cin, fbuf[n_halo:], C_, full, stream)
+                    if tail:
+                        resample_into(fin[full * Cin:], rem, fbuf[n_halo + full * C_:], tail, 1, stream)
+                    new = full * C_ + tail
+                else:
+                    self._pcm_to_float(raw_dev, sampwidth, channels, frames, fbuf[n_halo:], stream)
+                    new = frames
+                if new == 0:
+                    break
+                n_chunks = (new + C_ - 1) // C_
+                for k in range(n_chunks):                                    # reference :301, chunk by chunk
+                    total_time += (min((k + 1) * C_, new) - k * C_) / sr
+                n_tot = n_halo + new
                 c0, c1 = chunk_index, chunk_index + n_chunks
                 rec, _ = self._scan_batch(fbuf.data_ptr(), c0 * C_ - n_halo, n_tot, c0, c1, False)
                 self._emit_batch(rec, self._timestamps(rec), peak_times, events, on_pattern_detected)

@@ -1,8 +1,9 @@
 """Host-side audio helpers: WAV decode, FFT resampling, ffmpeg pipes.
 
 Mirrors the public helpers of the reference's audio_utils.py (file:line in each
-docstring).  Input decode is outside the detection hot path (SURVEY.md section 8f,
-rows N1/N2), so this is plain numpy host code.
+docstring).  Pattern-clip decode is outside the detection hot path, so this is plain numpy
+host code; the streaming side of rows N1/N2 runs on the
+device (csrc/pcm.cu, csrc/resample.cu, resample.py).
 """
 from __future__ import annotations
 
@@ -92,7 +93,7 @@ def resample_fft(x: NDArray[np.floating[Any]], num: int) -> NDArray[np.float32]:
     Y[:pos] = X[:pos]
     if neg:
         Y[num - neg:] = X[n - neg:]
-    return (np.fft.ifft(Y).real * (num / n)).astype(np.float32)
+    return (np.fft.ifft(Y, norm="forward").real * (1.0 / n)).astype(np.float32)     # lib.rs:268-274
 
 
 def resample_audio(audio: NDArray[np.float32], orig_sr: int, target_sr: int) -> NDArray[np.float32]:

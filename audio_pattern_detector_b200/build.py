@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["fft4.cu", "corr_inv.cu", "loudness.cu", "peaks.cu", "verify.cu", "pcm.cu", "api.cu"]
+SOURCES = ["fft4.cu", "corr_inv.cu", "loudness.cu", "peaks.cu", "verify.cu", "pcm.cu", "resample.cu", "api.cu"]
 LIB = os.path.join(HERE, "libapd_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -185,6 +185,11 @@ struct apd_ctx {
     KwConfig kw{};
     std::map<int, Fft4Plan> self_plans;
     long long launches = 0;
+    // opt-in (APD_B200_L2_PERSIST=1): the four-step intermediates of the two correlate streams are marked
+    // persisting in L2 (access-policy windows), so that with a small inv_units they never travel to HBM
+    bool l2_persist = false;
+    size_t l2_window_bytes = 0;           // bytes of each intermediate covered by its window
+    float l2_hit_ratio = 1.0f;
 
     // per-clip device tables
     int *d_clip_len = nullptr, *d_clip_group = nullptr, *d_strategy = nullptr, *d_is_short = nullptr;
@@ -657,6 +662,21 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(cudaMalloc(&c->d_unit_desc_b, corr_inv_desc_bytes(c->inv_units)));
     CK(dalloc(&c->d_scratch2, (size_t)c->n_slots * max_M));
     CK(cudaMalloc(&c->d_unit_desc2, corr_inv_desc_bytes(c->n_slots)));
+    if (const char* e = getenv("APD_B200_L2_PERSIST")) if (atoi(e)) {
+        int max_persist = 0, max_window = 0;
+        CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device));
+        CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device));
+        if (max_persist > 0 && max_window > 0) {
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+            const size_t want = (size_t)c->inv_units * (size_t)max_M * sizeof(float2);
+            c->l2_window_bytes = std::min(want, (size_t)max_window);
+            c->l2_hit_ratio = (float)std::min(1.0, (double)max_persist / (2.0 * (double)c->l2_window_bytes));
+            c->l2_persist = true;
+            if (getenv("APD_B200_VERBOSE"))
+                fprintf(stderr, "apd_b200: L2 persisting max %d B, window max %d B, intermediate %zu B x 2, hit ratio %.2f\n",
+                        max_persist, max_window, want, c->l2_hit_ratio);
+        }
+    }
     c->sel_capacity = B * n_clips;
     for (auto& b : c->sets) {
         CK(dalloc(&b.d_unit_max, (size_t)B * n_clips));
@@ -867,6 +887,17 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
         CK(cudaEventRecord(c->corr_fork, st));
         CK(cudaStreamWaitEvent(c->corr2, c->corr_fork, 0));
     }
+    if (c->l2_persist) {
+        cudaStreamAttrValue a{};
+        a.accessPolicyWindow.num_bytes = c->l2_window_bytes;
+        a.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
+        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        a.accessPolicyWindow.base_ptr = c->d_scratch;
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a));
+        a.accessPolicyWindow.base_ptr = c->d_scratch_b;
+        CK(cudaStreamSetAttribute(c->corr2, cudaStreamAttributeAccessPolicyWindow, &a));
+    }
     int launch = 0;
     for (auto& sc : c->shapes) {
         const int ns = (int)sc.clips.size();
@@ -886,6 +917,11 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
     if (two_streams) {
         CK(cudaEventRecord(c->corr_join, c->corr2));
         CK(cudaStreamWaitEvent(st, c->corr_join, 0));
+    }
+    if (c->l2_persist) {                  // the caller's stream goes back to normal caching for what follows
+        cudaStreamAttrValue a{};
+        a.accessPolicyWindow.num_bytes = 0;
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a));
     }
     CK(cudaGetLastError());
     return APD_OK;

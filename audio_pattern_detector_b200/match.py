@@ -155,10 +155,12 @@ class _WavFileStreamWrapper:
         self.needs_resample = self.input_sample_rate != target_sample_rate
         self._raw: Any = None
         self._raw_left = 0
-        # raw frames can go to the device as they are when no resampling is needed and the samples are 16/32-bit
-        # integers; the detector then widens them there (AudioPatternDetector._find_clip_in_pcm)
+        # raw 16/32-bit integer frames go to the device as they are; the detector widens them there and, when the
+        # file's rate differs from the detector's, resamples every chunk read there too (rows N1 / N2,
+        # AudioPatternDetector._find_clip_in_pcm)
         self.pcm_format = ((self._sampwidth, self._channels)
-                           if not self.needs_resample and self._sampwidth in (2, 4) and self._channels <= 8 else None)
+                           if self._sampwidth in (2, 4) and self._channels <= 8 else None)
+        self.pcm_sample_rate = self.input_sample_rate
         if self._channels != 1:
             print(f"Warning: WAV has {self._channels} channels, will be mixed to mono", file=sys.stderr)
 

@@ -150,6 +150,19 @@ APD_API int apd_profile_read(apd_ctx* ctx, double* ms4, int reset);
 APD_API int apd_pcm_to_float(const void* pcm_dev, int sample_width_bytes, int channels, int64_t n_frames,
                      float* out_dev, void* cuda_stream);
 
+/* FFT resampler (row N2): `batch` independent signals of n_in float32 samples each (signal b starts at
+ * in_dev + b*in_stride) -> n_out samples each (out_dev + b*out_stride), with the arithmetic of _native.resample
+ * (native-helper/src/python.rs:106-116 -> resample_1d, native-helper/src/lib.rs:235-275), which the reference applies
+ * per chunk read in _WavFileStreamWrapper.read (match.py:421-423) via audio_utils.resample_audio
+ * (audio_utils.py:154-171): float64 complex FFT of length n_in, the (N+1)/2 positive and (N-1)/2 negative bins of
+ * N = min(n_in, n_out) kept, inverse FFT of length n_out, scale 1/n_in, rounded to float32.  Any lengths up to
+ * 2^28 (7-smooth lengths as mixed-radix passes, others through Bluestein).  n_in == 0 gives zeros, n_in == n_out
+ * a copy.  The caller owns the float64 workspace (apd_resample_workspace_bytes; 0 for the trivial cases).
+ * Needs no context; returns APD_ERR_* without setting apd_last_error(). */
+APD_API int apd_resample_workspace_bytes(int64_t n_in, int64_t n_out, int32_t batch, int64_t* bytes);
+APD_API int apd_resample(const float* in_dev, int64_t n_in, int64_t in_stride, float* out_dev, int64_t n_out,
+                 int64_t out_stride, int32_t batch, void* workspace_dev, int64_t workspace_bytes, void* cuda_stream);
+
 /* Introspection for the bench: algorithmic byte counts and kernel launch counter. */
 APD_API int64_t apd_launch_count(apd_ctx* ctx);
 APD_API int apd_unit_n_out(apd_ctx* ctx, int32_t chunk, int32_t clip, int64_t total_samples, int32_t* n_out);

@@ -88,6 +88,28 @@ def loudness_normalize(data: Any, current_lufs: float, target_lufs: float) -> np
     return out
 
 
+def resample(data: Any, num_samples: int) -> np.ndarray:
+    """FFT resampling, restating resample_1d (native-helper/src/lib.rs:235-275; binding python.rs:106-116):
+    full complex float64 FFT, keep the (N+1)//2 lowest positive and (N-1)//2 lowest negative bins of
+    N = min(n, num_samples) -- an even N loses its Nyquist bin, unlike scipy.signal.resample -- un-normalised
+    inverse FFT of length num_samples, times 1/n, rounded to float32."""
+    x = _f32(data)
+    n, m = x.size, int(num_samples)
+    if n == 0 or m == 0:                                 # lib.rs:237-239
+        return np.zeros(m, dtype=np.float32)
+    if n == m:                                           # lib.rs:240-242
+        return x.copy()
+    spectrum = np.fft.fft(x.astype(np.float64))          # lib.rs:247-251
+    nc = min(n, m)
+    pos, neg = (nc + 1) // 2, (nc - 1) // 2              # lib.rs:258-260
+    new = np.zeros(m, dtype=np.complex128)
+    new[:pos] = spectrum[:pos]
+    if neg > 0:
+        new[m - neg:] = spectrum[n - neg:]
+    y = np.fft.ifft(new, norm="forward")                 # un-normalised inverse, lib.rs:268-269
+    return (y.real * (1.0 / n)).astype(np.float32)       # lib.rs:273-274
+
+
 def resample_preserve_maxima(data: Any, num_samples: int) -> np.ndarray:
     if num_samples == 0:
         raise ValueError("num_samples must be greater than 0")

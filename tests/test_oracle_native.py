@@ -73,6 +73,31 @@ def test_window_max_vectors():                           # lib.rs:892-966
         r(a([1, 2]), 0)
 
 
+def test_resample_kats():                                # lib.rs:855-890, bindings tests :154-189
+    from scipy.signal import resample as scipy_resample
+    r = native.resample
+    out = r(np.array([1, 2, 3, 4], np.float32), 4)
+    assert out.dtype == np.float32 and np.allclose(out, [1, 2, 3, 4], atol=1e-5)
+    assert r(np.zeros(0, np.float32), 0).size == 0
+    assert r(np.zeros(0, np.float32), 5).tolist() == [0.0] * 5
+    assert r(np.array([1, 2], np.float32), 0).size == 0
+    sine = np.sin(2.0 * np.float32(np.pi) * np.arange(8, dtype=np.float32) / np.float32(8)).astype(np.float32)
+    out = r(sine, 4)
+    assert out.size == 4 and abs(out[0]) < 0.1 and abs(out[1] - 1.0) < 0.1
+    assert r(np.array([0, 1, 0], np.float32), 6).size == 6
+    data = np.random.default_rng(99).standard_normal(160).astype(np.float32)
+    np.testing.assert_allclose(r(data, 80), scipy_resample(data, 80).astype(np.float32), atol=0.2)
+    data = np.array([0, 1, 0, -1, 0], np.float32)
+    np.testing.assert_allclose(r(data, 10), scipy_resample(data, 10).astype(np.float32), atol=1e-4)
+    out = r(np.array([1, 2, 3, 4], np.float64), 2)
+    assert out.dtype == np.float32 and out.size == 2
+    # the product's host-side clip loader (audio_utils.resample_fft) follows the same restatement
+    from audio_pattern_detector_b200.audio_utils import resample_fft
+    x = np.random.default_rng(5).standard_normal(1001).astype(np.float32)
+    for m in (500, 1000, 1002, 2003):
+        np.testing.assert_allclose(resample_fft(x, m), r(x, m), rtol=0, atol=1e-6)
+
+
 def test_k_weighting_and_loudness():                     # lib.rs:1015-1103, bindings :253-300
     bs, as_, bh, ah = native.k_weighting_coefficients(8000.0)
     assert abs(bs[0] - 1.32773315) < 1e-5 and as_[0] == 1.0
