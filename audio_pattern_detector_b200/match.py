@@ -23,6 +23,8 @@ from .audio_pattern_detector import AudioPatternDetector, PatternDetectedCallbac
 from .audio_utils import (DEFAULT_TARGET_SAMPLE_RATE, ffmpeg_get_float32_pcm, pcm_to_float32, resample_audio,
                           seconds_to_time)
 
+_READ_THREADS = 4          # positional-read threads per large file read (_WavFileStreamWrapper._pread)
+
 
 def _emit_jsonl(event_type: str, **fields: Any) -> None:
     """One JSON object per line, flushed (reference match.py:24-27)."""
@@ -155,6 +157,8 @@ class _WavFileStreamWrapper:
         self.needs_resample = self.input_sample_rate != target_sample_rate
         self._raw: Any = None
         self._raw_left = 0
+        self._raw_pos = 0
+        self._readers: Any = None
         # raw 16/32-bit integer frames go to the device as they are; the detector widens them there and, when the
         # file's rate differs from the detector's, resamples every chunk read there too (rows N1 / N2,
         # AudioPatternDetector._find_clip_in_pcm)
@@ -213,24 +217,56 @@ class _WavFileStreamWrapper:
                 size = struct.unpack("<I", hdr[4:])[0]
                 if hdr[:4] == b"data":
                     self._raw, self._raw_left = f, min(size, self._wav.getnframes() * self._sampwidth * self._channels)
+                    self._raw_pos = f.tell()
                     break
                 f.seek(size + (size & 1), 1)
         frame_bytes = self._sampwidth * self._channels
         want = min(frames * frame_bytes, self._raw_left)
         view = memoryview(buf).cast("B")[:want]
-        got = 0
-        while got < want:
-            k = self._raw.readinto(view[got:])
-            if not k:
-                break
-            got += k
+        got = self._pread(view)
         got -= got % frame_bytes
+        self._raw_pos += got
         self._raw_left -= got
         if got and not self._validated:
             self._validated = True
             if not any(view[:min(got, 1 << 20)]):
                 print("Warning: First chunk is all zeros - verify input is correct", file=sys.stderr)
         return got // frame_bytes
+
+    def _pread(self, view: memoryview) -> int:
+        """Fill ``view`` from the current position of the data chunk.  Large reads are cut into slices read by a
+        few threads with positional reads (``os.preadv`` releases the GIL): one thread copying from the page
+        cache into pinned memory runs at ~2 GB/s, well below what the device scans."""
+        want = len(view)
+        fd, pos = self._raw.fileno(), self._raw_pos
+        if want < (8 << 20):
+            parts = [(0, want)]
+        else:
+            k = min(_READ_THREADS, want >> 22)
+            step = (want // k + 4095) & ~4095
+            parts = [(a, min(a + step, want)) for a in range(0, want, step)]
+
+        def fill(part: tuple[int, int]) -> int:
+            a, b = part
+            done = a
+            while done < b:
+                r = os.preadv(fd, [view[done:b]], pos + done)
+                if r <= 0:
+                    break
+                done += r
+            return done - a
+
+        if len(parts) == 1:
+            return fill(parts[0])
+        if self._readers is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._readers = ThreadPoolExecutor(_READ_THREADS)
+        got = 0
+        for (a, b), r in zip(parts, self._readers.map(fill, parts)):
+            got += r
+            if r < b - a:                                                    # short read: the file ends here
+                break
+        return got
 
     def read_pcm(self, frames: int, /) -> bytes:
         """Raw interleaved PCM frames (only meaningful when ``pcm_format`` is set)."""
@@ -243,6 +279,9 @@ class _WavFileStreamWrapper:
 
     def close(self) -> None:
         self._wav.close()
+        if self._readers is not None:
+            self._readers.shutdown()
+            self._readers = None
         if self._raw is not None:
             self._raw.close()
             self._raw = None
