@@ -270,10 +270,19 @@ struct apd_ctx {
         int2* d_sel = nullptr;
         double *d_lufs = nullptr, *d_gain = nullptr;
         SectionGeom *d_geoms = nullptr, *h_geoms = nullptr;
+        // results of the sub-batch: per set, so that the marker-tone verification of one sub-batch (tone stream)
+        // can still be appending records while the side stream already verifies the next sub-batch
+        apd_candidate* d_out = nullptr;
+        apd_candidate* h_out = nullptr;   // pinned staging of d_out
+        void* d_tone_items = nullptr;
+        cudaEvent_t out_ready = nullptr;  // records and counters of the sub-batch are in h_out / h_counts
+        int n_expected = 0;
         int chunk_begin = 0, chunk_end = 0;
         cudaEvent_t p1_done = nullptr, loud_done = nullptr;
         cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    } sets[2];
+    } sets[3];
+    int n_sets = 2;                       // sets in use; APD_B200_SETS=3: the tone verification of a sub-batch also overlaps the
+                                          // normal phase 2 of the next one (measured: same step time)
     int cur_set = 0;
 
     // optional stage timing (CUDA events: [0..1] loudness stream, [2..4] caller's stream, [5..6] side stream)
@@ -288,6 +297,14 @@ struct apd_ctx {
     bool staged = false;
 };
 
+// the sets in use (the third exists only with APD_B200_SETS=3)
+struct UsedSets {
+    apd_ctx::BatchSet *b, *e;
+    apd_ctx::BatchSet* begin() const { return b; }
+    apd_ctx::BatchSet* end() const { return e; }
+};
+static UsedSets used_sets(apd_ctx* c) { return UsedSets{c->sets, c->sets + c->n_sets}; }
+
 static void use_set(apd_ctx* c, int k)
 {
     apd_ctx::BatchSet& cur = c->sets[c->cur_set];
@@ -297,6 +314,7 @@ static void use_set(apd_ctx* c, int k)
     c->d_spec = b.d_spec; c->d_unit_max = b.d_unit_max; c->d_unit_npeaks = b.d_unit_npeaks;
     c->d_counts = b.d_counts; c->h_counts = b.h_counts; c->d_sel = b.d_sel;
     c->d_lufs = b.d_lufs; c->d_gain = b.d_gain; c->d_geoms = b.d_geoms; c->h_geoms = b.h_geoms;
+    c->d_out = b.d_out; c->d_tone_items = b.d_tone_items;
     c->chunk_begin = b.chunk_begin; c->chunk_end = b.chunk_end;
     c->ev = b.ev;
     c->cur_set = k;
@@ -630,7 +648,8 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
 
     // ---- workspace
     const int B = c->maxB;
-    for (auto& b : c->sets) {
+    if (const char* e = getenv("APD_B200_SETS")) c->n_sets = std::min(3, std::max(2, atoi(e)));
+    for (auto& b : used_sets(c)) {
         CK(dalloc(&b.d_geoms, (size_t)G));
         CK(cudaMallocHost((void**)&b.h_geoms, sizeof(SectionGeom) * G));
     }
@@ -641,7 +660,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(dalloc(&c->d_kw_energy, (size_t)B * c->cells_stride));
     CK(dalloc(&c->d_kw_em1, (size_t)B));
     CK(dalloc(&c->d_kw_patch, (size_t)B * G * c->kw.patch_cells));
-    for (auto& b : c->sets) {
+    for (auto& b : used_sets(c)) {
         CK(dalloc(&b.d_lufs, (size_t)B * G));
         CK(dalloc(&b.d_gain, (size_t)B * G));
         CK(dalloc(&b.d_spec, (size_t)B * c->spec_slab));
@@ -678,7 +697,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         }
     }
     c->sel_capacity = B * n_clips;
-    for (auto& b : c->sets) {
+    for (auto& b : used_sets(c)) {
         CK(dalloc(&b.d_unit_max, (size_t)B * n_clips));
         CK(dalloc(&b.d_unit_npeaks, (size_t)B * n_clips));
         CK(dalloc(&b.d_counts, (size_t)S + 4));
@@ -718,18 +737,25 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(dalloc(&c->d_n_cands, (size_t)c->n_slots));
     CK(dalloc(&c->d_slot_cands, (size_t)c->n_slots * c->peak_stride));
     c->out_capacity = std::max(4096, B * n_clips * 4);
-    CK(dalloc(&c->d_out, (size_t)c->out_capacity));
+    for (auto& b : used_sets(c)) {
+        CK(dalloc(&b.d_out, (size_t)c->out_capacity));
+        CK(cudaMallocHost((void**)&b.h_out, sizeof(apd_candidate) * (size_t)c->out_capacity));
+        CK(cudaEventCreateWithFlags(&b.out_ready, cudaEventDisableTiming));
+    }
+    c->d_out = c->sets[c->cur_set].d_out;
     if (max_P > 0) {
         c->tone_stride = max_P;
         const long long per_cta = 3LL * 2 * max_P * (long long)sizeof(double2);
         c->tone_ctas = (int)std::max<long long>(1, std::min<long long>(64, (1LL << 31) / per_cta));
+        if (const char* e = getenv("APD_B200_TONE_ITEMS")) c->tone_ctas = std::max(1, std::min(c->tone_ctas, atoi(e)));
         CK(dalloc(&c->d_tone_scratch, (size_t)c->tone_ctas * 3 * 2 * max_P));
         CK(dalloc(&c->d_tone_stats, (size_t)c->tone_ctas * 3 * 4));
         c->tone_max_P = max_P;
         for (auto& cl : c->clips)
             if (cl.tone_P > 0) c->tone_max_L = std::max(c->tone_max_L, cl.L);
         c->tone_item_cap = std::max(4096, B * n_clips);
-        CK(cudaMalloc(&c->d_tone_items, tone_item_bytes() * c->tone_item_cap));
+        for (auto& b : used_sets(c)) CK(cudaMalloc(&b.d_tone_items, tone_item_bytes() * c->tone_item_cap));
+        c->d_tone_items = c->sets[c->cur_set].d_tone_items;
         CK(dalloc(&c->d_tone_metrics, (size_t)c->tone_item_cap * 15));
         const double wlr = std::nearbyint(0.025 * (double)sample_rate);
         c->tone_wl = wlr > 32.0 ? (int)wlr : 32;
@@ -760,6 +786,10 @@ extern "C" int apd_destroy(apd_ctx* c)
         for (void* q : sp) cudaFree(q);
         cudaFreeHost(b.h_counts);
         cudaFreeHost(b.h_geoms);
+        cudaFree(b.d_out);
+        cudaFree(b.d_tone_items);
+        cudaFreeHost(b.h_out);
+        if (b.out_ready) cudaEventDestroy(b.out_ready);
         if (b.p1_done) cudaEventDestroy(b.p1_done);
         if (b.loud_done) cudaEventDestroy(b.loud_done);
         for (auto& e : b.ev)
@@ -784,7 +814,7 @@ extern "C" int apd_destroy(apd_ctx* c)
                     c->d_clip_spec_off, c->d_kw_patch,
                     c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_scratch, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
-                    c->d_slot_cands, c->d_out, c->d_tone_scratch, c->d_tone_items, c->d_tone_metrics, c->d_tone_stats,
+                    c->d_slot_cands, c->d_tone_scratch, c->d_tone_metrics, c->d_tone_stats,
                     c->d_unit_desc};
     for (void* p : ptrs) cudaFree(p);
     delete c;
@@ -1022,12 +1052,17 @@ static bool cand_less(const apd_candidate& a, const apd_candidate& b)
     return a.peak < b.peak;
 }
 
-// Finish phase 2 of the batch in the current set on stream st: further rounds if more than n_slots units were
-// selected, the deferred tone verification, then results to host.  Appends to cand_host[*n_cand ...].
-static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
-                   double* lufs_host, cudaStream_t st)
+// Finish phase 2 of the batch in the current set, in two halves so that the marker-tone verification of one
+// sub-batch overlaps the normal verification of the next:
+//   collect_begin (side stream st): wait for the first phase-2 round, run further rounds if more than n_slots units
+//     were selected, then enqueue the deferred tone verification and the copy of records + counters to pinned
+//     host memory on the tone stream (every tone work item appends exactly one record, so the record count is
+//     known before the tone kernels run); records the set's out_ready event.
+//   collect_end: wait for out_ready, append the records to cand_host[*n_cand ...] and fill the optional traces.
+static int collect_begin(apd_ctx* c, cudaStream_t st)
 {
-    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size(), S = (int)c->shapes.size();
+    const int S = (int)c->shapes.size();
+    apd_ctx::BatchSet& set = c->sets[c->cur_set];
     CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (c->h_counts[S] > c->n_slots) {
@@ -1035,30 +1070,36 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
+    // the side stream is idle here (the host has just synchronised it), so the tone stream needs no event to
+    // see the work items; APD_B200_TONE_LOW=0 keeps the tone kernels on the side stream itself
     static const bool skip_tone = getenv("APD_B200_SKIP_TONE") && atoi(getenv("APD_B200_SKIP_TONE"));   // timing experiments
-    if (!skip_tone && c->h_counts[S + 3] > 0) {
-        static const bool tone_low = !(getenv("APD_B200_TONE_LOW") && !atoi(getenv("APD_B200_TONE_LOW")));
-        if (tone_low && st == c->side) {
-            CK(cudaEventRecord(c->tone_go, st));
-            CK(cudaStreamWaitEvent(c->tone, c->tone_go, 0));
-            phase2_tone(c, c->h_counts[S + 3], c->tone);
-            CK(cudaEventRecord(c->tone_done, c->tone));
-            CK(cudaStreamWaitEvent(st, c->tone_done, 0));
-        } else {
-            phase2_tone(c, c->h_counts[S + 3], st);
-        }
-    }
-    if (c->profile) cudaEventRecord(c->ev[6], st);
-    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    static const bool tone_low = !(getenv("APD_B200_TONE_LOW") && !atoi(getenv("APD_B200_TONE_LOW")));
+    cudaStream_t ts = (tone_low && st == c->side) ? c->tone : st;
+    const int n_tone = skip_tone ? 0 : c->h_counts[S + 3];
+    if (n_tone > 0) phase2_tone(c, n_tone, ts);
+    if (c->profile) cudaEventRecord(c->ev[6], ts);
+    set.n_expected = std::min(c->h_counts[S + 1] + n_tone, c->out_capacity);
+    CK(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * (S + 4), cudaMemcpyDeviceToHost, ts));
+    if (set.n_expected > 0)
+        CK(cudaMemcpyAsync(set.h_out, c->d_out, sizeof(apd_candidate) * (size_t)set.n_expected, cudaMemcpyDeviceToHost, ts));
+    CK(cudaEventRecord(set.out_ready, ts));
+    return APD_OK;
+}
+
+static int collect_end(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n_cand, apd_unit_trace* trace,
+                       double* lufs_host)
+{
+    const int B = c->chunk_end - c->chunk_begin, G = (int)c->groups.size(), S = (int)c->shapes.size();
+    apd_ctx::BatchSet& set = c->sets[c->cur_set];
+    cudaStream_t st = c->side;
+    CK(cudaEventSynchronize(set.out_ready));
     const int n = c->h_counts[S + 1];
     if (c->h_counts[S + 2]) return fail(APD_ERR_OVERFLOW, "candidate workspace overflow (flags " +
                                         std::to_string(c->h_counts[S + 2]) + ")");
+    if (n > set.n_expected) return fail(APD_ERR_OVERFLOW, "more candidate records than work items");
     if (*n_cand + n > cap) return fail(APD_ERR_OVERFLOW, "candidate buffer too small");
     apd_candidate* dst = cand_host + *n_cand;
-    if (n > 0) {
-        CK(cudaMemcpyAsync(dst, c->d_out, sizeof(apd_candidate) * n, cudaMemcpyDeviceToHost, st));
-    }
+    if (n > 0) memcpy(dst, set.h_out, sizeof(apd_candidate) * (size_t)n);
     std::vector<unsigned int> um;
     std::vector<int> np;
     if (trace) {
@@ -1072,7 +1113,7 @@ static int collect(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_t* n
         lf.resize((size_t)B * G);
         CK(cudaMemcpyAsync(lf.data(), c->d_lufs, sizeof(double) * lf.size(), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(st));
+    if (trace || lufs_host) CK(cudaStreamSynchronize(st));      // (waits for whatever phase 2 the side stream is running)
     std::sort(dst, dst + n, cand_less);
     *n_cand += n;
     if (trace) {
@@ -1126,7 +1167,7 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
     const bool prof = c->profile;
     int rc = APD_OK;
     auto phase1 = [&](int k) -> int {
-        use_set(c, k & 1);
+        use_set(c, k % c->n_sets);
         const int b0 = cb + k * c->maxB, b1 = std::min<int>(ce, b0 + c->maxB);
         // loudness on its own stream: enqueued while the previous sub-batch's correlate stage is still running
         int r = stage_begin(c, audio, base, n, b0, b1, s3);
@@ -1134,35 +1175,59 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
         if (prof) cudaEventRecord(c->ev[0], s3);
         if ((r = stage_loudness(c, s3))) return r;
         if (prof) cudaEventRecord(c->ev[1], s3);
-        CK(cudaEventRecord(c->sets[k & 1].loud_done, s3));
-        CK(cudaStreamWaitEvent(s1, c->sets[k & 1].loud_done, 0));
+        CK(cudaEventRecord(c->sets[k % c->n_sets].loud_done, s3));
+        CK(cudaStreamWaitEvent(s1, c->sets[k % c->n_sets].loud_done, 0));
         if (prof) cudaEventRecord(c->ev[2], s1);
         if ((r = stage_forward(c, s1))) return r;
         if (prof) cudaEventRecord(c->ev[3], s1);
         if ((r = stage_correlate_max(c, s1))) return r;
         if (prof) cudaEventRecord(c->ev[4], s1);
-        CK(cudaEventRecord(c->sets[k & 1].p1_done, s1));
+        CK(cudaEventRecord(c->sets[k % c->n_sets].p1_done, s1));
         return APD_OK;
     };
     auto phase2_begin = [&](int k) -> int {
-        use_set(c, k & 1);
-        CK(cudaStreamWaitEvent(s2, c->sets[k & 1].p1_done, 0));
+        use_set(c, k % c->n_sets);
+        CK(cudaStreamWaitEvent(s2, c->sets[k % c->n_sets].p1_done, 0));
         if (prof) cudaEventRecord(c->ev[5], s2);
         static const bool skip_p2 = getenv("APD_B200_SKIP_P2") && atoi(getenv("APD_B200_SKIP_P2"));   // timing experiments
         if (skip_p2) return APD_OK;
         return stage_peaks_verify(c, s2);
     };
-    auto phase2_end = [&](int k) -> int {
-        use_set(c, k & 1);
-        const size_t off = (size_t)(c->chunk_begin - cb) * c->n_clips;
-        return collect(c, cand_host, cap, n_cand, trace ? trace + off : nullptr, lufs_host ? lufs_host + off : nullptr, s2);
+    auto phase2_collect = [&](int k) -> int {
+        use_set(c, k % c->n_sets);
+        return collect_begin(c, s2);
     };
-    if ((rc = phase1(0)) || (rc = phase2_begin(0))) { cudaDeviceSynchronize(); return rc; }
-    for (int k = 1; k < nb; ++k) {
-        // enqueue the next sub-batch's phase 1 first so the GPU stays busy while the host waits for phase 2
-        if ((rc = phase1(k)) || (rc = phase2_end(k - 1)) || (rc = phase2_begin(k))) { cudaDeviceSynchronize(); return rc; }
+    auto phase2_end = [&](int k) -> int {
+        use_set(c, k % c->n_sets);
+        const size_t off = (size_t)(c->chunk_begin - cb) * c->n_clips;
+        return collect_end(c, cand_host, cap, n_cand, trace ? trace + off : nullptr, lufs_host ? lufs_host + off : nullptr);
+    };
+    // Host order.  With two sets (default) phase 2 of sub-batch k - 1, tone included, overlaps phase 1 of k and is
+    // finished before phase 2 of k starts.  With three sets (APD_B200_SETS=3) the marker-tone verification of k - 1
+    // (tone stream) also overlaps the normal phase 2 of k (side stream) and phase 1 of k + 1; the host collects the
+    // records of k - 2.  Measured equal: the GPU is work-conserving, phase 2 costs its SM / HBM time either way.
+    auto bail = [&](int r) { cudaDeviceSynchronize(); return r; };
+    if (c->n_sets == 3) {
+        for (int k = 0; k < std::min(2, nb); ++k)
+            if ((rc = phase1(k))) return bail(rc);
+        if ((rc = phase2_begin(0))) return bail(rc);
+        for (int k = 1; k < nb; ++k) {
+            if ((rc = phase2_collect(k - 1)) || (rc = phase2_begin(k))) return bail(rc);
+            if (k >= 2 && (rc = phase2_end(k - 2))) return bail(rc);
+            if (k + 1 < nb && (rc = phase1(k + 1))) return bail(rc);          // its set was that of k - 2
+        }
+        if ((rc = phase2_collect(nb - 1))) return bail(rc);
+        if (nb >= 2 && (rc = phase2_end(nb - 2))) return bail(rc);
+        rc = phase2_end(nb - 1);
+    } else {
+        if ((rc = phase1(0)) || (rc = phase2_begin(0))) return bail(rc);
+        for (int k = 1; k < nb; ++k) {
+            // enqueue the next sub-batch's phase 1 first so the GPU stays busy while the host waits for phase 2
+            if ((rc = phase1(k)) || (rc = phase2_collect(k - 1)) || (rc = phase2_end(k - 1)) || (rc = phase2_begin(k)))
+                return bail(rc);
+        }
+        if (!(rc = phase2_collect(nb - 1))) rc = phase2_end(nb - 1);
     }
-    rc = phase2_end(nb - 1);
     if (rc) cudaDeviceSynchronize();
     return rc;
 }
@@ -1207,7 +1272,7 @@ extern "C" int apd_profile(apd_ctx* c, int enable)
     if (!c) return fail(APD_ERR_INVALID, "apd_profile: null context");
     CK(cudaSetDevice(c->device));
     if (enable && !c->sets[0].ev[0])
-        for (auto& b : c->sets)
+        for (auto& b : used_sets(c))
             for (auto& e : b.ev) CK(cudaEventCreate(&e));
     c->profile = enable != 0;
     return APD_OK;

@@ -49,7 +49,8 @@ __device__ __forceinline__ void init_record(apd_candidate& r, int chunk, int cli
 // ---------------------------------------------------------------------------
 // normal + short clip
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_verify_normal(VerifyArgs A, int nslots)
 {
     __shared__ double red[32];
@@ -674,9 +675,17 @@ k_emit(VerifyArgs A, int nslots)
 void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches)
 {
     if (nslots <= 0) return;
-    // x: peaks of a unit in parallel (short clips can keep dozens); y: slots, strided (most slots are unused)
-    dim3 gn(32, std::min(nslots, 128));
-    k_verify_normal<<<gn, 1024, 0, st>>>(A, nslots);     // 1024 threads: a 10 s clip's slice is 160 k samples per pass
+    // x: peaks of a unit in parallel (short clips can keep dozens; the kernel strides); y: slots, strided (most
+    // slots are unused).  The CTA footprint decides how soon a CTA is placed while the correlate kernels own the SMs
+    // (three CTAs of ~20 K registers each per SM): 0 = 1024 threads x 63 registers (a whole SM must drain),
+    // 1 = 1024 x 32 (two correlate CTAs must retire), 2 = 512 x 40 (one), 3 = 256 x 63 (one).
+    static const int variant = getenv("APD_B200_VERIFY_CTA") ? atoi(getenv("APD_B200_VERIFY_CTA")) : 0;
+    static const int gx = getenv("APD_B200_VERIFY_GX") ? std::max(1, atoi(getenv("APD_B200_VERIFY_GX"))) : 32;
+    dim3 gn(gx, std::min(nslots, 128));
+    if (variant == 1) k_verify_normal<1024, 2><<<gn, 1024, 0, st>>>(A, nslots);
+    else if (variant == 2) k_verify_normal<512, 3><<<gn, 512, 0, st>>>(A, nslots);
+    else if (variant == 3) k_verify_normal<256, 4><<<gn, 256, 0, st>>>(A, nslots);
+    else k_verify_normal<1024, 1><<<gn, 1024, 0, st>>>(A, nslots);
     ++*launches;
 }
 
