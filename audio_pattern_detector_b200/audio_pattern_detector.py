@@ -427,7 +427,7 @@ class AudioPatternDetector:
         B200-side extension of the reference API: the stream is made device resident once and
         scanned ``max_batch_chunks`` chunks per launch sequence.
 
-        ``audio`` may also be interleaved integer PCM on the host (int16 / int32 array or tensor, ``pcm_channels``
+        ``audio`` may also be interleaved integer PCM on the host (int16 / int32 / uint8 array or tensor, ``pcm_channels``
         channels): the frames are copied as they are and widened to mono float32 on the device with the
         reference's arithmetic (row N1).
 
@@ -440,13 +440,13 @@ class AudioPatternDetector:
         host = None
         pcm_width = 0                     # > 0: host holds interleaved integer PCM frames (int16 / int32)
         if isinstance(audio, np.ndarray):
-            if audio.dtype in (np.int16, np.int32):
+            if audio.dtype in (np.int16, np.int32, np.uint8):
                 pcm_width = audio.dtype.itemsize
                 host = torch.from_numpy(np.ascontiguousarray(audio).reshape(-1))
             else:
                 host = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
         elif not audio.is_cuda:
-            if audio.dtype in (torch.int16, torch.int32):
+            if audio.dtype in (torch.int16, torch.int32, torch.uint8):
                 pcm_width = audio.element_size()
                 host = audio.contiguous().reshape(-1)
             else:
@@ -554,7 +554,7 @@ class AudioPatternDetector:
         samples out, row N2)."""
         torch = _torch()
         sampwidth, channels = src.pcm_format
-        np_dt, t_dt = (np.int16, torch.int16) if sampwidth == 2 else (np.int32, torch.int32)
+        np_dt, t_dt = {1: (np.uint8, torch.uint8), 2: (np.int16, torch.int16), 4: (np.int32, torch.int32)}[sampwidth]
         sr, C_ = self.target_sample_rate, self._chunk_samples
         in_sr = int(getattr(src, "pcm_sample_rate", None) or sr)
         resampling = in_sr != sr

@@ -127,6 +127,13 @@ class _WavStdinStreamWrapper:
         self._dtype = np.dtype(np.float32 if fmt == 3 else (np.int16 if bits == 16 else np.int32))
         label = "float32" if fmt == 3 else f"int{bits}"
         print(f"WAV stdin: {target_sample_rate}Hz, mono, {label}", file=sys.stderr)
+        # integer PCM goes to the device as it is and is widened there (AudioPatternDetector._find_clip_in_pcm);
+        # float32 WAV data needs no conversion at all and takes the float path
+        self.pcm_format = None if fmt == 3 else (self._dtype.itemsize, 1)
+
+    def read_pcm(self, frames: int, /) -> bytes:
+        """Raw PCM frames (blocks until ``frames`` frames or end of input, like the reference's read)."""
+        return sys.stdin.buffer.read(frames * self._dtype.itemsize)
 
     def read(self, size: int, /) -> bytes:
         data = sys.stdin.buffer.read((size // 4) * self._dtype.itemsize)
@@ -159,11 +166,11 @@ class _WavFileStreamWrapper:
         self._raw_left = 0
         self._raw_pos = 0
         self._readers: Any = None
-        # raw 16/32-bit integer frames go to the device as they are; the detector widens them there and, when the
+        # raw 8/16/32-bit integer frames go to the device as they are; the detector widens them there and, when the
         # file's rate differs from the detector's, resamples every chunk read there too (rows N1 / N2,
         # AudioPatternDetector._find_clip_in_pcm)
         self.pcm_format = ((self._sampwidth, self._channels)
-                           if self._sampwidth in (2, 4) and self._channels <= 8 else None)
+                           if self._sampwidth in (1, 2, 4) and self._channels <= 64 else None)
         self.pcm_sample_rate = self.input_sample_rate
         if self._channels != 1:
             print(f"Warning: WAV has {self._channels} channels, will be mixed to mono", file=sys.stderr)

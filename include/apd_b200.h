@@ -145,7 +145,8 @@ APD_API int apd_profile_read(apd_ctx* ctx, double* ms4, int reset);
 
 /* Streaming ingestion (row N1): integer PCM frames, already on the device, to mono float32 with the reference's
  * arithmetic (_WavFileStreamWrapper.read / _normalize_wav_data, match.py:393-427, audio_utils.py:60-79,132-151):
- * int16 / 32768 or int32 / 2^31, channels averaged in float32.  sample_width_bytes is 2 or 4, channels 1..8.
+ * int16 / 32768, int32 / 2^31 or (uint8 - 128) / 128, channels averaged in float32.  sample_width_bytes is 1, 2 or
+ * 4, channels 1..64.
  * Needs no context; returns APD_ERR_* without setting apd_last_error(). */
 APD_API int apd_pcm_to_float(const void* pcm_dev, int sample_width_bytes, int channels, int64_t n_frames,
                      float* out_dev, void* cuda_stream);
