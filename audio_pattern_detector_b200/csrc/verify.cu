@@ -319,11 +319,11 @@ __device__ __forceinline__ double2* tone_buf(const ToneRound& T, int r, int seg,
     return T.scratch + (((long long)r * 3 + seg) * 2 + which) * T.stride;
 }
 
-__device__ __forceinline__ int tone_npass(int P)      // radix-4 passes + one radix-2 pass if log2 P is odd
-{
-    const int lg = 31 - __clz(P);
-    return (lg >> 1) + (lg & 1);
-}
+// Pass schedule of the batched power-of-two float64 FFT: log2 P = 4 a + b  ->  a radix-16 passes, then one radix-4
+// pass if b >= 2, then one radix-2 pass if b is odd (P = 2^17: 16 16 16 16 2, five trips through memory instead of
+// the nine of a radix-4 schedule; the passes are bound by the traffic of the float64 ping-pong buffers).
+__host__ __device__ __forceinline__ int tone_npass_lg(int lg) { return (lg >> 2) + ((lg & 3) >= 2 ? 1 : 0) + (lg & 1); }
+__device__ __forceinline__ int tone_npass(int P) { return tone_npass_lg(31 - __clz(P)); }
 
 struct ToneSeg {
     const float* x;               // section start
@@ -369,6 +369,46 @@ k_tone_prep(VerifyArgs A, ToneRound T)
     }
 }
 
+// 16-point DFT in registers (4 x 4, constant inner twiddles), natural order in and out; INV conjugates.
+template <bool INV>
+__device__ __forceinline__ void zdft4(double2& a0, double2& a1, double2& a2, double2& a3)
+{
+    const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
+    const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
+    const double2 rr = INV ? make_double2(-d13.y, d13.x) : make_double2(d13.y, -d13.x);
+    a0 = make_double2(s02.x + s13.x, s02.y + s13.y);
+    a1 = make_double2(d02.x + rr.x, d02.y + rr.y);
+    a2 = make_double2(s02.x - s13.x, s02.y - s13.y);
+    a3 = make_double2(d02.x - rr.x, d02.y - rr.y);
+}
+template <bool INV>
+__device__ __forceinline__ double2 zmul_w16(double2 a, double c, double sn)     // a * (c - i sn), conjugated for INV
+{
+    const double s_ = INV ? sn : -sn;
+    return make_double2(a.x * c - a.y * s_, a.x * s_ + a.y * c);
+}
+template <bool INV>
+__device__ __forceinline__ void zdft16(double2* v)
+{
+    constexpr double c1 = 0.9238795325112867, s1 = 0.3826834323650898, h = 0.7071067811865476;
+    // r = 4 r1 + r2: DFT4 over r1 for every r2  ->  v[4 q1 + r2]
+#pragma unroll
+    for (int r2 = 0; r2 < 4; ++r2) zdft4<INV>(v[r2], v[4 + r2], v[8 + r2], v[12 + r2]);
+    // inner twiddles w16^{q1 r2}
+    v[5] = zmul_w16<INV>(v[5], c1, s1);
+    v[6] = zmul_w16<INV>(v[6], h, h);
+    v[7] = zmul_w16<INV>(v[7], s1, c1);
+    v[9] = zmul_w16<INV>(v[9], h, h);
+    v[10] = zmul_w16<INV>(v[10], 0.0, 1.0);
+    v[11] = zmul_w16<INV>(v[11], -h, h);
+    v[13] = zmul_w16<INV>(v[13], s1, c1);
+    v[14] = zmul_w16<INV>(v[14], -h, h);
+    v[15] = zmul_w16<INV>(v[15], -c1, -s1);
+    // DFT4 over r2 for every q1  ->  X[q1 + 4 q2] at v[4 q1 + q2]
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) zdft4<INV>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+}
+
 // One pass slot of the batched float64 FFT (see fft64 for the single-CTA variant used at init).
 template <bool INV>
 __global__ void __launch_bounds__(256)
@@ -379,41 +419,63 @@ k_tone_fft_pass(VerifyArgs A, ToneRound T, int slot)
     const int clip = T.items[T.i0 + r].clip;
     const int P = A.cv.tone_P[clip];
     const int lg = 31 - __clz(P);
-    const int r4 = lg >> 1, np = r4 + (lg & 1);
+    const int n16 = lg >> 2, has4 = (lg & 3) >= 2 ? 1 : 0, np = n16 + has4 + (lg & 1);
     if (slot >= np) return;
     const int start_b = INV ? (np & 1) : 0;                        // the inverse starts where the forward ended
     const double2* __restrict__ x = tone_buf(T, r, seg, (start_b + slot) & 1);
     double2* __restrict__ y = tone_buf(T, r, seg, (start_b + slot + 1) & 1);
     const double2* __restrict__ tw = A.cv.tone_tw[clip];
     const int half = P >> 1, quarter = P >> 2;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < quarter; j += gridDim.x * blockDim.x) {
-    if (slot < r4) {
-        const int Ns = 1 << (2 * slot);
-        const int tstep = P / (4 * Ns);
-        const int k = j & (Ns - 1);
-        const double2 a0 = x[j];
-        double2 a1 = x[j + quarter], a2 = x[j + 2 * quarter], a3 = x[j + 3 * quarter];
-        if (Ns > 1) {
-            a1 = zmul(a1, tw_at(tw, k * tstep, half, INV));
-            a2 = zmul(a2, tw_at(tw, 2 * k * tstep, half, INV));
-            a3 = zmul(a3, tw_at(tw, 3 * k * tstep, half, INV));
+    const int stride = gridDim.x * blockDim.x;
+    if (slot < n16) {                                               // radix 16, Ns = 16^slot
+        const int Ns = 1 << (4 * slot), T16 = P >> 4;
+        const int tstep = P / (16 * Ns);
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < T16; j += stride) {
+            const int k = j & (Ns - 1);
+            double2 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = x[j + q * T16];
+            if (Ns > 1) {
+                const double2 w1 = tw_at(tw, k * tstep, half, INV);
+                double2 w = w1;
+#pragma unroll
+                for (int q = 1; q < 16; ++q) {
+                    v[q] = zmul(v[q], w);
+                    if (q < 15) w = zmul(w, w1);
+                }
+            }
+            zdft16<INV>(v);
+            const int o = (j / Ns) * 16 * Ns + k;
+#pragma unroll
+            for (int q1 = 0; q1 < 4; ++q1)
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) y[o + (q1 + 4 * q2) * Ns] = v[4 * q1 + q2];
         }
-        const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
-        const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
-        const double2 rr = INV ? make_double2(-d13.y, d13.x) : make_double2(d13.y, -d13.x);
-        const int o = (j / Ns) * 4 * Ns + k;
-        y[o] = make_double2(s02.x + s13.x, s02.y + s13.y);
-        y[o + Ns] = make_double2(d02.x + rr.x, d02.y + rr.y);
-        y[o + 2 * Ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
-        y[o + 3 * Ns] = make_double2(d02.x - rr.x, d02.y - rr.y);
+    } else if (has4 && slot == n16) {                               // radix 4, Ns = 16^n16
+        const int Ns = 1 << (4 * n16);
+        const int tstep = P / (4 * Ns);
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < quarter; j += stride) {
+            const int k = j & (Ns - 1);
+            double2 a0 = x[j], a1 = x[j + quarter], a2 = x[j + 2 * quarter], a3 = x[j + 3 * quarter];
+            if (Ns > 1) {
+                a1 = zmul(a1, tw_at(tw, k * tstep, half, INV));
+                a2 = zmul(a2, tw_at(tw, 2 * k * tstep, half, INV));
+                a3 = zmul(a3, tw_at(tw, 3 * k * tstep, half, INV));
+            }
+            zdft4<INV>(a0, a1, a2, a3);
+            const int o = (j / Ns) * 4 * Ns + k;
+            y[o] = a0;
+            y[o + Ns] = a1;
+            y[o + 2 * Ns] = a2;
+            y[o + 3 * Ns] = a3;
+        }
     } else {                                                        // the single radix-2 pass (Ns = P/2)
-        for (int jj = j; jj < half; jj += quarter) {
+        for (int jj = blockIdx.x * blockDim.x + threadIdx.x; jj < half; jj += stride) {
             const double2 a = x[jj];
             const double2 b = zmul(x[jj + half], tw_at(tw, jj, half, INV));
             y[jj] = make_double2(a.x + b.x, a.y + b.y);
             y[jj + half] = make_double2(a.x - b.x, a.y - b.y);
         }
-    }
     }
 }
 
@@ -709,7 +771,8 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
     }
     int lg = 0;
     while ((1 << lg) < max_P) ++lg;
-    const int max_pass = (lg >> 1) + (lg & 1);
+    int max_pass = 0;                                              // a shorter transform may need more passes
+    for (int l = 1; l <= lg; ++l) max_pass = std::max(max_pass, tone_npass_lg(l));
     const int hop = wl / 2 > 1 ? wl / 2 : 1;
     const int nf_max = max_L - wl > 0 ? (max_L - wl + hop - 1) / hop : 0;
     const long long work_max = (long long)nf_max * (wl / 2 + 1);
