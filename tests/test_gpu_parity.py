@@ -205,3 +205,18 @@ def test_tma_staged_row_pass_variant_matches():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_three_set_pipeline_matches(monkeypatch):
+    """APD_B200_SETS=3: the tone verification of a sub-batch overlaps the normal phase 2 of the next one (records and
+    tone work items per set).  Same candidates, scores and order as the default two-set pipeline, with tone clips
+    in the mix and one chunk per sub-batch so that every hand-over happens many times."""
+    run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c10"][0]
+    clips, audio = synthetic_inputs(run)
+    assert any(c.get("strategy") == "marker_tone" for c in clips)
+    want = make_detector(clips, 8000, 10, max_batch_chunks=1).scan_array(audio, collect_trace=True)
+    monkeypatch.setenv("APD_B200_SETS", "3")
+    got = make_detector(clips, 8000, 10, max_batch_chunks=1).scan_array(audio, collect_trace=True)
+    assert got.peak_times == want.peak_times and got.events == want.events
+    assert got.records.tobytes() == want.records.tobytes()
+    assert got.unit_trace == want.unit_trace
