@@ -135,3 +135,28 @@ def test_resampling_wav_stream_matches_the_host_path(tmp_path, in_rate):
     dev.close()
     assert sum(len(v) for v in times_h.values()) > 0
     assert times_d == times_h and seen_d == seen_h and total_d == total_h
+
+
+@pytest.mark.parametrize("frames", [1, 5, 160001])
+def test_resampling_stream_edge_lengths(tmp_path, frames):
+    """Files shorter than one chunk read: a single frame resamples to nothing (the reference's read() then returns
+    b"" = end of stream), a handful of frames to a 2-sample final chunk, and one chunk plus one frame to a full chunk
+    and nothing."""
+    from audio_pattern_detector_b200.audio_clip import AudioStream
+    from audio_pattern_detector_b200.match import _WavFileStreamWrapper
+    run = [r for r in load_json("synthetic_runs.json") if r["case"]["id"] == "s8k_c10"][0]
+    clips, audio = synthetic_inputs(run)
+    up = native.resample(audio[:80000], 160000)
+    pcm = np.clip(np.round(np.resize(up, frames) * 32768.0), -32768, 32767).astype(np.int16)
+    path = tmp_path / "short.wav"
+    write_wav(path, pcm, 16000)
+    det = make_detector(clips, 8000, 10, max_batch_chunks=2)
+    out = []
+    for device_path in (False, True):
+        w = _WavFileStreamWrapper(str(path), 8000)
+        if not device_path:
+            w.pcm_format = None
+        out.append(det.find_clip_in_audio(AudioStream(name="s", audio_stream=w, sample_rate=8000)))
+        w.close()
+    assert out[0] == out[1]
+    assert out[1][1] == {1: 0.0, 5: 2 / 8000, 160001: 10.0}[frames]
