@@ -220,3 +220,17 @@ def test_three_set_pipeline_matches(monkeypatch):
     assert got.peak_times == want.peak_times and got.events == want.events
     assert got.records.tobytes() == want.records.tobytes()
     assert got.unit_trace == want.unit_trace
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf"), -float("inf")])
+def test_non_finite_samples(bad):
+    """A float stream with a NaN / Inf sample (a corrupt float32 WAV): the K-weighting filter state stays non-finite
+    for the rest of the section, every block fails the gates, the gain becomes infinite and the section saturates --
+    whatever the reference's arithmetic gives (lib.rs:128-227, apd.py:489-490), the device gives the same, and the
+    chunks after the look-back has left the bad sample behind are unaffected."""
+    run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c10"][0]
+    clips, audio = synthetic_inputs(run)
+    audio = audio.copy()
+    audio[10 * 8000 + 4321] = bad                                        # inside chunk 1
+    out = compare_with_oracle(clips, audio, 8000, 10, max_batch_chunks=4)
+    assert out["accepted"] > 0
