@@ -259,6 +259,9 @@ struct apd_ctx {
     cudaEvent_t corr_fork = nullptr, corr_join = nullptr;
     float2* d_scratch_b = nullptr;        // second four-step intermediate / descriptor set for that stream
     void* d_unit_desc_b = nullptr;
+    cudaStream_t fwd = nullptr;           // opt-in (APD_B200_FWD_STREAM=1): forward FFT of the next sub-batch, own scratch, beside
+                                          // the correlate stage of the current one
+    float2* d_scratch_fwd = nullptr;      // four-step intermediate of the forward FFT (= d_scratch unless that stream is on)
     cudaStream_t tone = nullptr;          // deferred marker-tone verification: bandwidth-heavy f64 FFT passes, at the
                                           // caller's (low) priority so that they fill the tails of the correlate launches
     cudaEvent_t scan_start = nullptr, tone_go = nullptr, tone_done = nullptr;
@@ -279,13 +282,15 @@ struct apd_ctx {
         int n_expected = 0;
         int chunk_begin = 0, chunk_end = 0;
         cudaEvent_t p1_done = nullptr, loud_done = nullptr;
-        cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t fwd_done = nullptr;
+        cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     } sets[3];
     int n_sets = 2;                       // sets in use; APD_B200_SETS=3: the tone verification of a sub-batch also overlaps the
                                           // normal phase 2 of the next one (measured: same step time)
     int cur_set = 0;
 
-    // optional stage timing (CUDA events: [0..1] loudness stream, [2..4] caller's stream, [5..6] side stream)
+    // optional stage timing (CUDA events: [0..1] loudness stream, [2..3] forward FFT, [7]..[4] correlate stage on the
+    // caller's stream, [5..6] phase 2)
     bool profile = false;
     cudaEvent_t* ev = nullptr;
     double stage_ms[4] = {0, 0, 0, 0};
@@ -676,6 +681,13 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     }
     c->scratch_elems = std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
+    c->d_scratch_fwd = c->d_scratch;
+    if (const char* e = getenv("APD_B200_FWD_STREAM")) if (atoi(e)) {
+        CK(dalloc(&c->d_scratch_fwd, (size_t)B * (size_t)max_class_groups * (size_t)max_M));
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->fwd, cudaStreamNonBlocking, atoi(e) == 2 ? lo : hi));
+    }
     CK(cudaMalloc(&c->d_unit_desc, corr_inv_desc_bytes(c->inv_units)));
     CK(dalloc(&c->d_scratch_b, (size_t)c->inv_units * max_M));
     CK(cudaMalloc(&c->d_unit_desc_b, corr_inv_desc_bytes(c->inv_units)));
@@ -704,6 +716,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         CK(cudaMallocHost((void**)&b.h_counts, sizeof(int) * (S + 4)));
         CK(dalloc(&b.d_sel, (size_t)c->sel_capacity));
         CK(cudaEventCreateWithFlags(&b.p1_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b.fwd_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b.loud_done, cudaEventDisableTiming));
     }
     {
@@ -791,10 +804,13 @@ extern "C" int apd_destroy(apd_ctx* c)
         cudaFreeHost(b.h_out);
         if (b.out_ready) cudaEventDestroy(b.out_ready);
         if (b.p1_done) cudaEventDestroy(b.p1_done);
+        if (b.fwd_done) cudaEventDestroy(b.fwd_done);
         if (b.loud_done) cudaEventDestroy(b.loud_done);
         for (auto& e : b.ev)
             if (e) cudaEventDestroy(e);
     }
+    if (c->fwd) cudaStreamDestroy(c->fwd);
+    if (c->d_scratch_fwd != c->d_scratch) cudaFree(c->d_scratch_fwd);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->pre) cudaStreamDestroy(c->pre);
     if (c->tone) cudaStreamDestroy(c->tone);
@@ -889,14 +905,14 @@ static int stage_forward(apd_ctx* c, cudaStream_t st)
         if (corr_inv_supported(sc.plan)) {
             // all sliding-window groups of the shape in one pair of launches
             FwdGroups FG{sc.d_group_halo, sc.d_group_index, sc.d_group_spec_off, (int)sc.groups.size()};
-            launch_forward(sc.plan, c->h_geoms[sc.groups[0]], FG, c->d_gain, G, B, c->d_scratch, c->d_spec,
+            launch_forward(sc.plan, c->h_geoms[sc.groups[0]], FG, c->d_gain, G, B, c->d_scratch_fwd, c->d_spec,
                            c->spec_slab, st);
             c->launches += 2;
             continue;
         }
         for (int g : sc.groups) {
             launch_forward(sc.plan, c->h_geoms[g], FwdGroups{nullptr, nullptr, nullptr, 0}, c->d_gain + g, G, B,
-                           c->d_scratch, c->d_spec + c->groups[g].spec_off, c->spec_slab, st);
+                           c->d_scratch_fwd, c->d_spec + c->groups[g].spec_off, c->spec_slab, st);
             c->launches += 2;
         }
     }
@@ -1136,7 +1152,7 @@ static int collect_end(apd_ctx* c, apd_candidate* cand_host, int32_t cap, int32_
             for (int p = 0; p < c->n_clips; ++p)
                 lufs_host[(size_t)ci * c->n_clips + p] = lf[(size_t)ci * G + c->clips[p].group];
     if (c->profile) {
-        const int pairs[4][2] = {{0, 1}, {2, 3}, {3, 4}, {5, 6}};
+        const int pairs[4][2] = {{0, 1}, {2, 3}, {7, 4}, {5, 6}};
         for (int i = 0; i < 4; ++i) {
             float ms = 0.0f;
             if (cudaEventElapsedTime(&ms, c->ev[pairs[i][0]], c->ev[pairs[i][1]]) == cudaSuccess) c->stage_ms[i] += ms;
@@ -1176,10 +1192,16 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
         if ((r = stage_loudness(c, s3))) return r;
         if (prof) cudaEventRecord(c->ev[1], s3);
         CK(cudaEventRecord(c->sets[k % c->n_sets].loud_done, s3));
-        CK(cudaStreamWaitEvent(s1, c->sets[k % c->n_sets].loud_done, 0));
-        if (prof) cudaEventRecord(c->ev[2], s1);
-        if ((r = stage_forward(c, s1))) return r;
-        if (prof) cudaEventRecord(c->ev[3], s1);
+        cudaStream_t sf = c->fwd ? c->fwd : s1;
+        CK(cudaStreamWaitEvent(sf, c->sets[k % c->n_sets].loud_done, 0));
+        if (prof) cudaEventRecord(c->ev[2], sf);
+        if ((r = stage_forward(c, sf))) return r;
+        if (prof) cudaEventRecord(c->ev[3], sf);
+        if (c->fwd) {
+            CK(cudaEventRecord(c->sets[k % c->n_sets].fwd_done, sf));
+            CK(cudaStreamWaitEvent(s1, c->sets[k % c->n_sets].fwd_done, 0));
+        }
+        if (prof) cudaEventRecord(c->ev[7], s1);
         if ((r = stage_correlate_max(c, s1))) return r;
         if (prof) cudaEventRecord(c->ev[4], s1);
         CK(cudaEventRecord(c->sets[k % c->n_sets].p1_done, s1));

@@ -65,10 +65,10 @@ __device__ __forceinline__ double warp_sum(double v)
 // f64 multiply, clamp to [-1, 1] (NaN survives the clamp), round to f32, NaN -> 0.
 __device__ __forceinline__ float normalize_sample(float x, double gain)
 {
-    double v = (double)x * gain;
-    if (v != v) return 0.0f;
-    v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
-    return (float)v;
+    // the clamp is applied after the rounding to float32: rounding is monotonic and +-1 are exact, so
+    // clamp(round(v)) == round(clamp(v)), and it keeps the compares off the float64 pipe
+    const float r = (float)((double)x * gain);
+    return r != r ? 0.0f : fminf(fmaxf(r, -1.0f), 1.0f);
 }
 
 }  // namespace apd
