@@ -79,6 +79,30 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int) -> None:
+    """One process per GPU: run (and therefore first-touch / pin host memory) on the CPUs of the NUMA node the GPU's
+    PCIe root hangs off, so that the H2D copies of the e2e arm do not cross sockets.  Best effort, Linux only."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus: set[int] = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:  # noqa: BLE001 - affinity is an optimisation, never a requirement
+        pass
+
+
 def cpu_oracle_rate(patterns, audio_np: np.ndarray, n_chunks: int, procs: int) -> tuple[float, float, int]:
     """Oracle port (oracle/detector.py) over chunks [1, 1+n_chunks) of audio_np, sharded over `procs`
     processes (each chunk keeps its look-back halo).  Returns (audio-hours/s, seconds, units)."""
@@ -164,6 +188,7 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        bind_to_gpu_numa_node(local)      # before any pinned allocation: host buffers on the GPU's own socket
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     from audio_pattern_detector_b200 import workloads as W
