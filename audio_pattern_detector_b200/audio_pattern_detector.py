@@ -480,10 +480,14 @@ class AudioPatternDetector:
             # one apd_scan per segment: the C side cuts a segment into sub-batches of max_batch_chunks chunks
             # and overlaps phase 2 of one sub-batch with phase 1 of the next
             if host is not None:
-                # a short first segment (its copy is the only one not hidden), then long ones
-                seg = self._max_batch * 8
-                head = min(last, first + self._max_batch)
-                bounds = [first] + list(range(head, last, seg)) + [last] if head < last else [first, last]
+                # a short first segment (its copy is the only one not hidden), then segments that double in length
+                # up to a cap: the copy of segment i + 1 runs while segment i is scanned, and a pinned H2D copy moves
+                # a chunk about twice as fast as the device scans one, so doubling keeps every later copy hidden
+                cap = self._max_batch * int(os.environ.get("APD_B200_HOST_SEG", 8))
+                bounds, step = [first], self._max_batch
+                while bounds[-1] < last:
+                    bounds.append(min(last, bounds[-1] + step))
+                    step = min(2 * step, cap)
             else:
                 bounds = [first, last]
             if last <= first:
