@@ -578,29 +578,32 @@ class AudioPatternDetector:
             pins = [torch.empty(per_read * Cin * channels, dtype=t_dt).pin_memory() for _ in range(2)]
             raw_dev = torch.empty_like(pins[0], device=dev)
 
-            def read_batch(which: int) -> int:
-                """One large read of up to per_read chunks into pinned buffer `which`; returns the frames read.
+            def read_batch(which: int, chunks: int) -> int:
+                """One large read of up to `chunks` chunks into pinned buffer `which`; returns the frames read.
                 Runs on the reader thread, overlapped with the device scan of the previous batch (apd_scan
                 releases the GIL)."""
                 if hasattr(src, "readinto_pcm"):                              # straight into pinned memory
-                    return src.readinto_pcm(pins[which].numpy(), per_read * Cin)
-                data = src.read_pcm(per_read * Cin)
+                    return src.readinto_pcm(pins[which].numpy(), chunks * Cin)
+                data = src.read_pcm(chunks * Cin)
                 got = len(data) // (sampwidth * channels)
                 if got:
                     pins[which].numpy()[:got * channels] = np.frombuffer(data, dtype=np_dt, count=got * channels)
                 return got
 
+            # the first read is the only one the device waits for: keep it short, then double up to per_read
             n_halo, chunk_index, which = 0, 0, 0
-            pending = pool.submit(read_batch, which)
+            want = min(per_read, self._max_batch)
+            pending = pool.submit(read_batch, which, want)
             while True:
                 frames = pending.result()
                 if frames == 0:
                     break
-                last = frames < per_read * Cin                               # a short read ends the stream
+                last = frames < want * Cin                                   # a short read ends the stream
                 cur = which
                 if not last:
                     which ^= 1
-                    pending = pool.submit(read_batch, which)                 # next batch while this one is scanned
+                    want = min(per_read, 2 * want)
+                    pending = pool.submit(read_batch, which, want)           # next batch while this one is scanned
                 raw_dev[:frames * channels].copy_(pins[cur][:frames * channels], non_blocking=True)
                 if resampling:
                     from .resample import resample_into
