@@ -49,8 +49,7 @@ __device__ __forceinline__ void init_record(apd_candidate& r, int chunk, int cli
 // ---------------------------------------------------------------------------
 // normal + short clip
 // ---------------------------------------------------------------------------
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
+__global__ void __launch_bounds__(1024)
 k_verify_normal(VerifyArgs A, int nslots)
 {
     __shared__ double red[32];
@@ -738,16 +737,11 @@ void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* 
 {
     if (nslots <= 0) return;
     // x: peaks of a unit in parallel (short clips can keep dozens; the kernel strides); y: slots, strided (most
-    // slots are unused).  The CTA footprint decides how soon a CTA is placed while the correlate kernels own the SMs
-    // (three CTAs of ~20 K registers each per SM): 0 = 1024 threads x 63 registers (a whole SM must drain),
-    // 1 = 1024 x 32 (two correlate CTAs must retire), 2 = 512 x 40 (one), 3 = 256 x 63 (one).
-    static const int variant = getenv("APD_B200_VERIFY_CTA") ? atoi(getenv("APD_B200_VERIFY_CTA")) : 0;
-    static const int gx = getenv("APD_B200_VERIFY_GX") ? std::max(1, atoi(getenv("APD_B200_VERIFY_GX"))) : 32;
-    dim3 gn(gx, std::min(nslots, 128));
-    if (variant == 1) k_verify_normal<1024, 2><<<gn, 1024, 0, st>>>(A, nslots);
-    else if (variant == 2) k_verify_normal<512, 3><<<gn, 512, 0, st>>>(A, nslots);
-    else if (variant == 3) k_verify_normal<256, 4><<<gn, 256, 0, st>>>(A, nslots);
-    else k_verify_normal<1024, 1><<<gn, 1024, 0, st>>>(A, nslots);
+    // slots are unused).  1024 threads: a 10 s clip's slice is 160 k samples per pass.  Smaller CTA footprints
+    // (1024 x 32 registers, 512 x 40, 256 x 63) and a 4x smaller grid were measured: no change of the step time
+    // (DESIGN.md section 6).
+    dim3 gn(32, std::min(nslots, 128));
+    k_verify_normal<<<gn, 1024, 0, st>>>(A, nslots);
     ++*launches;
 }
 
