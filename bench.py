@@ -180,6 +180,11 @@ def main() -> None:
         run_reference(args)
         return
 
+    # stdout carries exactly one JSON line: whatever native libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,7 +329,8 @@ def main() -> None:
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"chunks 1..{nck} of the same stream x 64 patterns ({units} units), "
                                               f"{dt:.1f} s wall; oracle port of the reference's scipy-style CPU path"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
