@@ -570,6 +570,8 @@ class AudioPatternDetector:
         dev = f"cuda:{self._device}"
         cap = self._max_halo + self._stream_read_chunks * C_
         from concurrent.futures import ThreadPoolExecutor
+
+        from .resample import resample_into
         per_read = self._stream_read_chunks
         with torch.cuda.device(self._device), ThreadPoolExecutor(1) as pool:
             stream = torch.cuda.current_stream()
@@ -606,7 +608,6 @@ class AudioPatternDetector:
                     pending = pool.submit(read_batch, which, want)           # next batch while this one is scanned
                 raw_dev[:frames * channels].copy_(pins[cur][:frames * channels], non_blocking=True)
                 if resampling:
-                    from .resample import resample_into
                     self._pcm_to_float(raw_dev, sampwidth, channels, frames, fin, stream)
                     full, rem = divmod(frames, Cin)
                     tail = int(rem * sr / in_sr)                             # audio_utils.py:170

@@ -39,8 +39,8 @@ def resample_into(src: Any, n_in: int, dst: Any, n_out: int, batch: int = 1, str
     need = workspace_bytes(n_in, n_out, sub)
     ws = _workspace.get(dev)
     if ws is None or ws.numel() < need:
+        _workspace.pop(dev, None)                  # release the smaller buffer before allocating the larger one
         ws = None
-        _workspace[dev] = None
         ws = _workspace[dev] = torch.empty(max(need, 16), dtype=torch.uint8, device=src.device)
     L = _lib.lib()
     for b0 in range(0, batch, sub):
