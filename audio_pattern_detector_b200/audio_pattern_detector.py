@@ -41,6 +41,22 @@ DEFAULT_BATCH_CHUNKS = 32
 PatternDetectedCallback = Callable[[str, float], None]
 
 
+class ClipData(TypedDict):
+    """Per-clip data of the reference class (:42-48).  Here it lives on the device (apd_create); ``clip_info()``
+    copies it back in this layout for inspection and parity tests."""
+    clip: NDArray[np.float32]
+    clip_name: str
+    sliding_window: int
+    correlation_clip: NDArray[np.float32]
+    correlation_clip_absolute_max: "np.floating[Any]"
+
+
+class ClipCache(TypedDict):
+    """The reference's lazily filled cache of down-sampled clip curves (:51-54); computed eagerly on the device."""
+    downsampled_correlation_clips: dict[str, NDArray[np.float32]]
+    downsampled_pearson_windows: dict[str, list[NDArray[np.float32]]]
+
+
 class ClipConfig(TypedDict):
     duration_seconds: float
     sliding_window_seconds: int

@@ -156,6 +156,29 @@ def ffmpeg_get_float32_pcm(full_audio_path: str, target_sample_rate: int | None 
             proc.stdout.close()
 
 
+def write_wav_file(filepath: str, audio_data: NDArray[np.float32], sample_rate: int) -> None:
+    """Mono float32 samples -> a file in whatever container ffmpeg picks from the name (reference
+    audio_utils.py:294-322); ``ValueError`` when ffmpeg fails."""
+    cmd = ["ffmpeg", "-y", "-f", "f32le", "-ar", str(sample_rate), "-ac", "1", "-i", "pipe:", "-loglevel", "error",
+           filepath]
+    proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL)
+    proc.communicate(input=np.ascontiguousarray(audio_data, dtype=np.float32).tobytes())
+    if proc.returncode != 0:
+        raise ValueError(f"ffmpeg write failed with return code {proc.returncode}")
+
+
+def get_audio_duration(audio_path: str) -> float | None:
+    """Duration in seconds from ffprobe, ``None`` when the source has none, e.g. a live stream (reference
+    audio_utils.py:324-352)."""
+    import json
+    res = subprocess.run(["ffprobe", "-v", "error", "-show_entries", "format=duration", "-of", "json", audio_path],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise ValueError(f"ffprobe failed: {res.stderr}")
+    duration = json.loads(res.stdout).get("format", {}).get("duration")
+    return None if duration is None else float(duration)
+
+
 def seconds_to_time(seconds: float, include_decimals: bool = True) -> str:
     """HH:MM:SS[.mmm].  Stands in for andrew_utils.seconds_to_time (a dependency absent from the
     reference tree; its format is pinned only by README.md:89-93 "00:00:05.500")."""

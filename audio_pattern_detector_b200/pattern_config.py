@@ -92,7 +92,10 @@ def load_apd_file(path: str | Path, sample_rate: int) -> PatternConfig:
     kind = _need(clip, "source", str, where)
     if kind not in VALID_CLIP_SOURCES:
         raise ValueError(f"{where}: unknown [clip].source '{kind}'. Valid sources: {sorted(VALID_CLIP_SOURCES)}")
-    _reject_unknown(clip, _CLIP_FIELDS[kind] | {"source"}, where, f"[clip] (source='{kind}')")
+    extra = sorted(set(clip) - _CLIP_FIELDS[kind] - {"source"})
+    if extra:                                                            # reference pattern_config.py:88-93,114-119
+        raise ValueError(f"{where}: unknown [clip] field(s) for source='{kind}': {extra}. "
+                         f"Valid fields: {sorted(_CLIP_FIELDS[kind])}")
     audio = _sine(clip, sample_rate, where) if kind == "sine" else _wav_base64(clip, sample_rate, where)
 
     ver = _need(doc, "verification", dict, where)
