@@ -33,10 +33,10 @@ SR = 8000
 SPC = 60
 N_PATTERNS = 64
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel pair from the committed ncu --set full
-# capture (profiles/ncu_r1_corr_summary.txt), scaled from the captured launches to one step; None until captured
-# captured (profiles/ncu_r1_corr_summary.txt): one 512-unit launch pair of the 640 x 512 shape moves 3.238 GB
-# (k_corr_rows 0.443 r + 1.285 w, k_corr_cols2 1.505 r + 0.006 w) = 6.32 MB/unit; the 512 x 512 shape scales with M
-TRAFFIC_BYTES_PER_STEP = int(49 * 1440 * 3.238e9 / 512 + 15 * 1440 * 3.238e9 / 512 * 0.8)
+# capture (profiles/ncu_r1_end_corr_summary.txt, end of round 1; profiles/ncu_r1_corr_summary.txt earlier: 3.238 GB),
+# scaled from the captured launches to one step: one 512-unit launch pair of the 640 x 512 shape moves 3.265 GB
+# (k_corr_rows 0.443 r + 1.284 w, k_corr_cols2 1.534 r + 0.004 w) = 6.38 MB/unit; the 512 x 512 shape scales with M
+TRAFFIC_BYTES_PER_STEP = int(49 * 1440 * 3.265e9 / 512 + 15 * 1440 * 3.265e9 / 512 * 0.8)
 
 
 def measured_peak_gbs() -> tuple[float, str]:
