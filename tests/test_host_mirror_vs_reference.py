@@ -80,3 +80,97 @@ def test_slicing_with_zero_padding(mods):
         w, m = int(rng.integers(1, 30)), int(rng.integers(-5, 45))
         assert same(ref["audio_utils"].slicing_with_zero_padding(arr, w, m),
                     own["audio_utils"].slicing_with_zero_padding(arr, w, m)), (arr.size, w, m)
+
+
+def _capture(fn):
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        fn()
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("fmt", ["both", "ms", "formatted"])
+def test_jsonl_events_are_identical(mods, fmt):
+    """match.py:524-565: pattern_detected / end events, the per-clip suppression of consecutive equal milliseconds,
+    non-ASCII clip names."""
+    ref, own = mods
+    events = [("cbs_news", 25.89875), ("cbs_news", 25.8990), ("天空下的彩虹intro", 13.848), ("cbs_news", 25.8994),
+              ("cbs_news", 3725.0004), ("x", 0.0), ("x", 0.0004), ("x", 0.0005), ("x", 86399.9996)]
+
+    def run(m):
+        cb = m._make_jsonl_callback(fmt)
+        for n, t in events:
+            cb(n, t)
+        m._emit_jsonl_end(7325.4321, fmt)
+        m._emit_jsonl("start", source="日本語.wav")
+
+    assert _capture(lambda: run(ref["match"])) == _capture(lambda: run(own["match"]))
+
+
+def _wav_header(fmt_tag=1, channels=1, rate=8000, bits=16, extra=b"", data=b"\x00" * 8):
+    import struct
+    fmt = struct.pack("<HHIIHH", fmt_tag, channels, rate, rate * channels * bits // 8, channels * bits // 8, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + extra + b"data" + struct.pack("<I", len(data)) + data
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def test_wav_header_validation_is_identical(mods):
+    """match.py:215-283: accepted formats and every rejection message."""
+    import io
+    import struct
+    ref, own = mods
+    junk = b"LIST" + struct.pack("<I", 4) + b"abcd"
+    cases = [_wav_header(), _wav_header(bits=32), _wav_header(fmt_tag=3, bits=32), _wav_header(extra=junk),
+             _wav_header(bits=8), _wav_header(fmt_tag=3, bits=64), _wav_header(fmt_tag=2), _wav_header(channels=2),
+             _wav_header(rate=16000), b"RIFX" + _wav_header()[4:], _wav_header()[:8] + b"WAVX" + _wav_header()[12:],
+             _wav_header()[:20], _wav_header()[:12], b""]
+    for blob in cases:
+        out = []
+        for m in (ref["match"], own["match"]):
+            try:
+                out.append(("ok", m._validate_wav_header(io.BytesIO(blob), 8000)))
+            except ValueError as e:
+                out.append(("ValueError", str(e)))
+        assert out[0] == out[1], blob[:40]
+
+
+def test_multiplexed_pattern_protocol_is_identical(mods, monkeypatch):
+    """match.py:30-96: [uint32 n] then [uint32 name_len][name][uint32 data_len][wav] per pattern."""
+    import io
+    import struct
+    import sys
+    import types
+    import wave
+    ref, own = mods
+
+    def wav_bytes(rate):
+        b = io.BytesIO()
+        with wave.open(b, "wb") as w:
+            w.setnchannels(1)
+            w.setsampwidth(2)
+            w.setframerate(rate)
+            w.writeframes((np.sin(np.arange(1600) * 0.3) * 12000).astype(np.int16).tobytes())
+        return b.getvalue()
+
+    def frame(items):
+        out = struct.pack("<I", len(items))
+        for name, blob in items:
+            nb = name.encode("utf-8")
+            out += struct.pack("<I", len(nb)) + nb + struct.pack("<I", len(blob)) + blob
+        return out
+
+    good = frame([("beep", wav_bytes(8000)), ("彩虹", wav_bytes(16000))])
+    streams = [good, good[:30], frame([]), frame([("a", wav_bytes(8000)), ("a", wav_bytes(8000))]),
+               struct.pack("<I", 1) + struct.pack("<I", 0), b"\x01\x00"]
+    for blob in streams:
+        out = []
+        for m in (ref["match"], own["match"]):
+            monkeypatch.setattr(sys, "stdin", types.SimpleNamespace(buffer=io.BytesIO(blob)))
+            try:
+                clips = m._read_patterns_from_multiplexed_stdin(8000)
+                out.append([(c.name, c.audio.tobytes(), c.sample_rate) for c in clips])
+            except ValueError as e:
+                out.append(("ValueError", str(e)))
+        assert out[0] == out[1], blob[:24]
