@@ -174,3 +174,30 @@ def test_multiplexed_pattern_protocol_is_identical(mods, monkeypatch):
             except ValueError as e:
                 out.append(("ValueError", str(e)))
         assert out[0] == out[1], blob[:24]
+
+
+def test_detector_argument_validation_is_identical(mods):
+    """apd.py:105-137: duplicate names, wrong clip sample rate, chunk too small -- the same ValueError text, raised
+    before anything touches the device (so this runs without a GPU)."""
+    ref, own = mods
+    rdet = importlib.import_module("audio_pattern_detector.audio_pattern_detector").AudioPatternDetector
+    odet = importlib.import_module("audio_pattern_detector_b200.audio_pattern_detector").AudioPatternDetector
+    tone = (0.3 * np.sin(np.arange(20000) * 0.7)).astype(np.float32)
+
+    def clips(m, spec):
+        return [m["audio_clip"].AudioClip(name=n, audio=tone[:k].copy(), sample_rate=sr) for n, k, sr in spec]
+
+    bad = [
+        ([("a", 8000, 8000), ("a", 4000, 8000)], dict()),                                  # duplicate name
+        ([("a", 8000, 16000)], dict()),                                                     # clip at another rate
+        ([("a", 8000, 8000)], dict(target_sample_rate=16000)),
+        ([("a", 20000, 8000)], dict(seconds_per_chunk=5)),                                  # 2.5 s clip needs >= 6 s
+        ([("ok", 8000, 8000), ("long", 16001, 8000)], dict(seconds_per_chunk=4)),
+    ]
+    for spec, kw in bad:
+        out = []
+        for m, det in ((ref, rdet), (own, odet)):
+            with pytest.raises(ValueError) as e:
+                det(audio_clips=clips(m, spec), **kw)
+            out.append(str(e.value))
+        assert out[0] == out[1], (spec, kw)
