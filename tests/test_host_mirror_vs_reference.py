@@ -201,3 +201,20 @@ def test_detector_argument_validation_is_identical(mods):
                 det(audio_clips=clips(m, spec), **kw)
             out.append(str(e.value))
         assert out[0] == out[1], (spec, kw)
+
+
+def test_match_pattern_argument_errors_are_identical(mods, tmp_path):
+    """match.py:120-149: missing audio, missing pattern, no patterns, unknown pattern type -- before any device work."""
+    ref, own = mods
+    audio = sorted(glob.glob(BASE + "/*.wav"))[0]
+    clip = sorted(glob.glob(BASE + "/clips/*.wav"))[0]
+    empty = tmp_path / "empty_dir"
+    empty.mkdir()
+    cases = [("/nonexistent/audio.wav", [clip]), (audio, ["/nonexistent/clip.wav"]), (audio, [])]
+    for src, pats in cases:
+        out = []
+        for m in (ref["match"], own["match"]):
+            with pytest.raises(ValueError) as e:
+                m.match_pattern(src, pats)
+            out.append(str(e.value))
+        assert out[0] == out[1], (src, pats)
