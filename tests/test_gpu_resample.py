@@ -5,6 +5,7 @@ path of the same wrapper.
 Tolerance: both sides compute in float64 and round once to float32, so outputs are identical except where the
 float64 value sits within ~1e-13 of a float32 rounding boundary: at most 1 float32 ulp of the signal's peak, on a
 vanishing fraction of samples."""
+import os
 import wave
 
 import numpy as np
@@ -160,3 +161,29 @@ def test_resampling_stream_edge_lengths(tmp_path, frames):
         w.close()
     assert out[0] == out[1]
     assert out[1][1] == {1: 0.0, 5: 2 / 8000, 160001: 10.0}[frames]
+
+
+RESAMPLE_RUNS = load_json("resample_runs.json")
+
+
+@pytest.mark.parametrize("run", RESAMPLE_RUNS, ids=lambda r: f"{os.path.basename(r['wav'])}/{r['spc']}")
+def test_resampling_stream_matches_the_reference_golden(tmp_path, run):
+    """End to end against the UNMODIFIED reference: its match_pattern on the 16 kHz fixtures with an 8 kHz detector
+    (every chunk read resampled, match.py:395-423) gave tests/golden/resample_runs.json (oracle/make_golden_resample.py);
+    here the same WAV goes through the device PCM + resampler path."""
+    from audio_pattern_detector_b200.audio_clip import AudioStream
+    from audio_pattern_detector_b200.match import _WavFileStreamWrapper
+    from tests.golden_util import fixture_clips, fixtures
+    meta = [r for r in load_json("fixture_runs.json") if r["sr"] == 8000 and len(r["clips"]) >= 6][0]
+    clips = fixture_clips(meta)
+    assert sorted(c["name"] for c in clips) == sorted(run["timestamps"])
+    path = tmp_path / "in16k.wav"
+    write_wav(path, fixtures()["wav:" + run["wav"]], run["wav_rate"])
+    det = make_detector(clips, 8000, run["spc"], max_batch_chunks=2)
+    w = _WavFileStreamWrapper(str(path), 8000)
+    assert w.pcm_format == (2, 1) and w.pcm_sample_rate == 16000
+    seen = []
+    times, total = det.find_clip_in_audio(AudioStream(name="s", audio_stream=w, sample_rate=8000),
+                                          on_pattern_detected=lambda n, t: seen.append([n, t]))
+    w.close()
+    assert times == run["timestamps"] and seen == run["events"] and total == run["total_time"]
