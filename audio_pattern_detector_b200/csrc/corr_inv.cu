@@ -222,6 +222,131 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
     rows_item<kRowsPerCta, KEEP_H>(buf, D, by * per, min(nunits, (by + 1) * per), bx, M, W + (long long)(by * per) * M);
 }
 
+// ---------------------------------------------------------------- rows, two passes (opt-in, APD_B200_ROWS2=1)
+// 512 = 32 x 16 with ONE shared-memory exchange instead of two (tools/proto_two_pass.py):
+// 16 threads per row, thread j owns the 32 elements e = j + 16 s at load and at store time (every global access of
+// a half-warp is one contiguous 128-byte run); pass 1 is one radix-32 butterfly per thread (Ns = 1, no twiddles),
+// pass 2 two radix-16 butterflies per thread (t = j and t = j + 16) whose inter-pass twiddles w_512^{t r} and
+// four-step twiddles w_M^{(t + 32 q) c} are powers of hoisted bases, rebuilt per unit by a depth-4 product tree.
+// The 16 threads of a row sit in one warp, so the exchange needs __syncwarp only: no block or named barriers.
+// Exchange layout (conflict-free 64-bit accesses): element 32 jj + q of a row lives at 32 jj + (q ^ jj).
+__device__ __forceinline__ c2 mul_root32(c2 x, int k)          // x * e^{+2 pi i k / 32}, k a compile-time constant
+{
+    constexpr float c[24] = {1.0f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f,
+                             0.195090322f, 0.0f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f,
+                             -0.831469612f, -0.923879533f, -0.98078528f, -1.0f, -0.98078528f, -0.923879533f,
+                             -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f};
+    constexpr float sn[24] = {0.0f, 0.195090322f, 0.382683432f, 0.555570233f, 0.707106781f, 0.831469612f, 0.923879533f,
+                              0.98078528f, 1.0f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f,
+                              0.382683432f, 0.195090322f, 0.0f, -0.195090322f, -0.382683432f, -0.555570233f,
+                              -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f};
+    if (k == 0) return x;
+    if (k == 8) return rot_p(x);
+    return cmul(x, c[k], sn[k]);
+}
+// inverse (sign +) DFTs of 32 = 4 x 8 and 16 = 4 x 4 points in registers, natural order in and out
+__device__ __forceinline__ void idft32(c2* v)
+{
+    c2 y[4][8];
+#pragma unroll
+    for (int r2 = 0; r2 < 8; ++r2) {                                  // DFT4 over r1 of v[8 r1 + r2]
+        c2 t[4] = {v[r2], v[8 + r2], v[16 + r2], v[24 + r2]};
+        Dft2<4, +1>::run(t);
+#pragma unroll
+        for (int q1 = 0; q1 < 4; ++q1) y[q1][r2] = mul_root32(t[q1], q1 * r2);
+    }
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) {                                  // DFT8 over r2 -> X[q1 + 4 q2]
+        Dft2<8, +1>::run(y[q1]);
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2) v[q1 + 4 * q2] = y[q1][q2];
+    }
+}
+__device__ __forceinline__ void idft16(c2* v)
+{
+    c2 y[4][4];
+#pragma unroll
+    for (int r2 = 0; r2 < 4; ++r2) {
+        c2 t[4] = {v[r2], v[4 + r2], v[8 + r2], v[12 + r2]};
+        Dft2<4, +1>::run(t);
+#pragma unroll
+        for (int q1 = 0; q1 < 4; ++q1) y[q1][r2] = mul_root32(t[q1], 2 * q1 * r2);
+    }
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) {
+        Dft2<4, +1>::run(y[q1]);
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) v[q1 + 4 * q2] = y[q1][q2];
+    }
+}
+// p[r] = w^r, r < 16, by a product tree (depth 4) in packed arithmetic
+__device__ __forceinline__ void powers16(c2 w, c2* p)
+{
+    p[0] = mk(1.0f, 0.0f);
+    p[1] = w;
+#pragma unroll
+    for (int r = 2; r < 16; ++r) p[r] = cmul(p[r >> 1], p[r - (r >> 1)]);
+}
+
+constexpr int kRows2PerCta = 8;           // 16 threads per row -> 128 threads, 32 KB of shared memory
+
+__global__ void __launch_bounds__(kRows2PerCta * 16, 3)
+k_corr_rows2(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+{
+    __shared__ __align__(1024) c2 buf[kRows2PerCta * kN2];
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int u_begin = by * per, u_end = min(nunits, (by + 1) * per);
+    const int q = threadIdx.x >> 4, j = threadIdx.x & 15;
+    const int c = bx * kRows2PerCta + q;                                   // row of the N1 x 512 matrix
+    const unsigned rb = smem_addr(buf + q * kN2);
+    const unsigned st_base = rb + 8u * (unsigned)(32 * j);                 // + 8 * (q2 ^ j)
+    const float invM = 1.0f / (float)M;
+    // hoisted bases: inter-pass twiddle w_512^t and four-step twiddle w_M^{t c} for t = j, j + 16; step w_M^{32 c}
+    c2 wt[2], f0[2];
+#pragma unroll
+    for (int u2 = 0; u2 < 2; ++u2) {
+        const int t = j + 16 * u2;
+        wt[u2] = from_f2(cispif(2.0f * (float)t * (1.0f / 512.0f)));
+        f0[u2] = from_f2(twiddle_frac(t * c, invM, +1.0f));
+    }
+    const c2 fstep = from_f2(twiddle_frac(32 * c, invM, +1.0f));
+    const long long row_off = (long long)c * kN2 + j;
+    float2* __restrict__ Wg = W + (long long)u_begin * M;
+    for (int u = u_begin; u < u_end; ++u) {
+        const UnitDesc d = load_desc(D + u);
+        if (d.n_out < 0) continue;
+        const c2* __restrict__ xs = reinterpret_cast<const c2*>(d.xs + row_off);
+        const c2* __restrict__ hs = reinterpret_cast<const c2*>(d.hs + row_off);
+        c2 v[32];
+#pragma unroll
+        for (int s_ = 0; s_ < 32; ++s_) v[s_] = ldg_stream(xs + 16 * s_);
+#pragma unroll
+        for (int s_ = 0; s_ < 32; ++s_) v[s_] = cmul(v[s_], ldg_nc(hs + 16 * s_));
+        idft32(v);                                                         // butterfly j of T = 16: outputs 32 j + q2
+#pragma unroll
+        for (int q2 = 0; q2 < 32; ++q2) sts(st_base + 8u * (unsigned)(q2 ^ j), v[q2]);
+        __syncwarp();
+        c2 fq[16];
+        powers16(fstep, fq);
+        c2* __restrict__ out = reinterpret_cast<c2*>(Wg + (long long)(u - u_begin) * M + row_off);
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+            const int t = j + 16 * u2;
+            c2 z[16], p[16];
+            // element (jj = r, q2 = t) sits at 32 r + (t ^ r)
+#pragma unroll
+            for (int r = 0; r < 16; ++r) z[r] = lds<0>(rb + 8u * (unsigned)(32 * r + (t ^ r)));
+            powers16(wt[u2], p);
+#pragma unroll
+            for (int r = 1; r < 16; ++r) z[r] = cmul(z[r], p[r]);
+            idft16(z);                                                     // outputs e = t + 32 q
+#pragma unroll
+            for (int qq = 0; qq < 16; ++qq) out[16 * u2 + 32 * qq] = cmul(z[qq], cmul(f0[u2], fq[qq]));
+        }
+        __syncwarp();
+    }
+}
+
 // Dense phase-1 launches: section-spectrum rows staged by TMA bulk copies (64 KB of dynamic shared memory per CTA).
 __global__ void __launch_bounds__(kRowsPerCta * 64, 3)
 k_corr_rows_tma(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
@@ -658,6 +783,8 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
     // opt-in: measured 3 % slower than the register prefetch (profiles/sweeps_r1.txt) -- the row pass already runs at
     // ~70 % of the HBM copy bandwidth and the staged rows cost an extra shared-memory read per element
     static const int rows_tma = env_int2("APD_B200_ROWS_TMA", 0);
+    // opt-in two-pass row kernel (one exchange, 16 threads per row); phase 1 only
+    static const int rows2 = env_int2("APD_B200_ROWS2", 0);
     if (rows_tma && !write && U.list == nullptr) {
         // dense launch: every unit position is in use, so the staging pipeline needs no holes
         constexpr size_t kSmem = (size_t)kRowsPerCta * 4 * kN2 * sizeof(c2) + kRowsPerCta * 2 * sizeof(unsigned long long);
@@ -667,6 +794,10 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
             attr = true;
         }
         k_corr_rows_tma<<<gr, kRowsPerCta * 64, kSmem, st>>>(D, nunits, per, P.M, scratch, swap);
+    } else if (rows2 && !write) {
+        const int tiles2 = P.N1 / kRows2PerCta;
+        const dim3 gr2 = swap ? dim3(ny, tiles2) : dim3(tiles2, ny);
+        k_corr_rows2<<<gr2, kRows2PerCta * 16, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     } else if (keep_h) k_corr_rows<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     else k_corr_rows<false><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     static const int cols2 = env_int2("APD_B200_COLS2", 1);

@@ -234,3 +234,22 @@ def test_non_finite_samples(bad):
     audio[10 * 8000 + 4321] = bad                                        # inside chunk 1
     out = compare_with_oracle(clips, audio, 8000, 10, max_batch_chunks=4)
     assert out["accepted"] > 0
+
+
+def test_two_pass_row_kernel_variant_matches():
+    """The opt-in two-pass row kernel (APD_B200_ROWS2=1: 512 = 32 x 16, one shared-memory exchange, 16 threads per
+    row) gives the same detections and scores."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import os; os.environ['APD_B200_ROWS2'] = '1'\n"
+        "from tests.golden_util import load_json, synthetic_inputs\n"
+        "from tests.gpu_compare import compare_with_oracle\n"
+        "run = [r for r in load_json('synthetic_runs.json') if r['case']['id'] == 's8k_c60'][0]\n"
+        "clips, audio = synthetic_inputs(run); c = run['case']\n"
+        "out = compare_with_oracle(clips, audio, c['sr'], c['spc'], c.get('height_min'), max_batch_chunks=4)\n"
+        "print('OK', out['units'], out['accepted'])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
