@@ -290,7 +290,7 @@ __device__ __forceinline__ void powers16(c2 w, c2* p)
 
 constexpr int kRows2PerCta = 8;           // 16 threads per row -> 128 threads, 32 KB of shared memory
 
-__global__ void __launch_bounds__(kRows2PerCta * 16, 3)
+__global__ void __launch_bounds__(kRows2PerCta * 16, 4)
 k_corr_rows2(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
 {
     __shared__ __align__(1024) c2 buf[kRows2PerCta * kN2];
