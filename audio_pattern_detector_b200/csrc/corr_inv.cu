@@ -16,6 +16,14 @@
 // invariants of the per-CTA loop over units: the XOR-swizzled exchange layouts (fft_fast.cuh) reduce to
 // "thread constant + immediate" for loads and "thread constant ^ immediate" for stores.
 #include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <map>
+#include <utility>
+
+#include <cuda.h>
 
 #include "fft_fast.cuh"
 #include "internal.h"
@@ -216,6 +224,15 @@ __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ 
 template <bool KEEP_H>
 __global__ void __launch_bounds__(kRowsPerCta * 64, KEEP_H ? 2 : 3)
 k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+{
+    __shared__ __align__(1024) c2 buf[kRowsPerCta * 2 * kN2];
+    const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    rows_item<kRowsPerCta, KEEP_H>(buf, D, by * per, min(nunits, (by + 1) * per), bx, M, W + (long long)(by * per) * M);
+}
+
+template <bool KEEP_H>
+__global__ void __launch_bounds__(kRowsPerCta * 64, 3)
+k_corr_rows3(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
 {
     __shared__ __align__(1024) c2 buf[kRowsPerCta * 2 * kN2];
     const int bx = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
@@ -636,6 +653,280 @@ k_corr_cols2(const UnitDesc* __restrict__ D, int nunits, int per, int M, const f
     cols2_item<S>(raw, red, D, u0, min(nunits, u0 + per), bx, M, W + (long long)u0 * M, unit_max_bits);
 }
 
+// ---------------------------------------------------------------- tiled intermediate (TMA in / TMA out)
+// The four-step intermediate W of a unit is kept in 128-byte pieces: piece (ct, t) holds rows c = 4 ct .. 4 ct + 3 of
+// columns b = 4 t .. 4 t + 3,
+//     W[((c >> 2) * 128 + (b >> 2)) * 16 + (((c & 3) ^ ((b >> 2) & 3)) << 2) + (b & 3)],
+// so that (a) the row pass, whose CTA owns four rows, stages its 16 KB of output in shared memory in exactly this
+// order (the XOR makes the staging stores conflict-free) and hands it to ONE bulk shared->global copy per unit,
+// and (b) the column pass, whose CTA owns four columns, fetches its N1 x 4 tile with ONE TMA tensor copy of
+// N1/4 pieces.  Neither transfer passes through the LSU data pipe, which bounds both kernels: a column-pass
+// LDG.128 touched 16 lines (32 bytes of each), a row-pass STG cost twice the wavefronts of an STS.
+constexpr int kWTiles = kN2 / 4;                 // 128 column tiles
+constexpr int kWBlock = kWTiles * 16;            // complex elements of one block of four rows (16 KB)
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_tile(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bytes, unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_tile3(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bytes, unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+// the N1 x 4 tile `tile` of launch-local unit u: tiled layout (2-D map, N1/4 pieces of 128 bytes) or plain row-major
+// layout (3-D map over [8][N1/8][512], N1 pieces of 32 bytes)
+template <bool TILED, int N1>
+__device__ __forceinline__ void tma_in(unsigned dst, const CUtensorMap* map, int tile, int u, unsigned bytes, unsigned bar)
+{
+    if (TILED) tma_load_tile(dst, map, tile * 16, u * (N1 / 4), bytes, bar);
+    else tma_load_tile3(dst, map, tile * 4, 0, u * 8, bytes, bar);
+}
+
+// Row pass, tiled output.  Same passes as rows_item; the last pass writes to a double-buffered staging area.
+template <bool KEEP_H>
+__global__ void __launch_bounds__(kRowsPerCta * 64, 3)
+k_corr_rows_t(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* __restrict__ W, int swap)
+{
+    extern __shared__ unsigned char rows_t_smem[];
+    c2* buf = reinterpret_cast<c2*>((reinterpret_cast<uintptr_t>(rows_t_smem) + 1023) & ~uintptr_t(1023));
+    const int tile = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int u_begin = by * per, u_end = min(nunits, (by + 1) * per);
+    float2* __restrict__ Wg = W + (long long)u_begin * M + (long long)tile * kWBlock;
+    const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
+    const int c = tile * kRowsPerCta + q;
+    const RowAddr<8> A(smem_addr(buf + q * (2 * kN2)), j);
+    constexpr unsigned kB = kN2 * 8u;
+    // staging: two buffers of kWBlock elements behind the exchange buffers; output r of this thread is column
+    // b = j + 64 r, i.e. piece t = (j >> 2) + 16 r, slot q ^ (t & 3), word j & 3
+    const unsigned stage0 = smem_addr(buf + kRowsPerCta * 2 * kN2);
+    const unsigned st_out = stage0 + 128u * (unsigned)(j >> 2) + 32u * (unsigned)(q ^ ((j >> 2) & 3)) + 8u * (unsigned)(j & 3);
+    constexpr unsigned kStageB = kWBlock * 8u;
+    float2 tw2[8], tw3[8], fs[8];
+    pass_twiddles<8, +1, 8>(j, tw2);
+    pass_twiddles<8, +1, 64>(j, tw3);
+    {
+        const float invM = 1.0f / (float)M;
+        geometric<8>(twiddle_frac(j * c, invM, +1.0f), twiddle_frac(64 * c, invM, +1.0f), fs);
+    }
+    const long long row_off = (long long)c * kN2 + j;
+    const float2* cur_hs = nullptr;
+    c2 h[8], xn[8];
+    UnitDesc dn = load_desc(D + u_begin);
+    if (dn.n_out >= 0) {
+        const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
+    }
+    int k = 0;                                             // units staged so far
+    for (int u = u_begin; u < u_end; ++u) {
+        const UnitDesc d = dn;
+        const bool more = u + 1 < u_end;
+        if (more) dn = load_desc(D + u + 1);
+        if (d.n_out < 0) {
+            if (more && dn.n_out >= 0) {
+                const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
+            }
+            continue;
+        }
+        const c2* __restrict__ hs = reinterpret_cast<const c2*>(d.hs + row_off);
+        c2 v[8];
+        if (KEEP_H) {
+            if (d.hs != cur_hs) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) h[r] = ldg_nc(hs + 64 * r);
+                cur_hs = d.hs;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = cmul(xn[r], h[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = cmul(xn[r], ldg_nc(hs + 64 * r));
+        }
+        Dft2<8, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts(A.st1 ^ (8u * r), v[r]);
+        if (more && dn.n_out >= 0) {
+            const c2* __restrict__ xs = reinterpret_cast<const c2*>(dn.xs + row_off);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) xn[r] = ldg_stream(xs + 64 * r);
+        }
+        group_sync<64>(q + 1);
+        APD_ROW_LOAD8(A, 0, v)
+        bfly_tw<8>(v, tw2);
+        Dft2<8, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts((A.st2 + kB) ^ (72u * r), v[r]);
+        group_sync<64>(q + 1);
+        APD_ROW_LOAD8(A, kB, v)
+        bfly_tw<8>(v, tw3);
+        Dft2<8, +1>::run(v);
+        const unsigned so = st_out + (k & 1) * kStageB;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts(so + 2048u * r, cmul(v[r], fs[r]));
+        fence_proxy_async_smem();                          // staged words visible to the bulk-copy engine
+        // the copy that last read the OTHER staging buffer has finished reading before anybody passes this barrier
+        if (threadIdx.x == 0) bulk_wait_read0();
+        __syncthreads();
+        if (threadIdx.x == 0) bulk_store(Wg + (long long)(u - u_begin) * M, stage0 + (k & 1) * kStageB, kStageB);
+        ++k;
+    }
+    if (threadIdx.x == 0) bulk_wait_read0();
+}
+
+// Column pass, tiled input: the N1 x 4 tile of unit u arrives by one TMA tensor copy (box 16 x N1/4 of 8-byte
+// elements) on an mbarrier; two columns per thread as in cols2_item.  NS input buffers: with one, the next unit's
+// tile is requested after the first exchange (its latency is covered by two passes); with two, a whole unit ahead.
+// WRITE: normalised correlation written out (phase 2) with the arithmetic of the maximum (phase 1), so that the
+// phase-2 values divided by max(self max, phase-1 max) reproduce that maximum bit for bit.
+template <class S, bool WRITE, int NS, bool TILED>
+__global__ void __launch_bounds__(2 * (S::N / 8), WRITE ? 2 : (S::N == 512 ? 4 : 3))
+k_corr_cols_t(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict__ D, int nunits, int per, int M,
+              unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride, int swap)
+{
+    constexpr int N1 = S::N;
+    constexpr int T1 = N1 / 8;
+    constexpr int R2 = S::R2;
+    constexpr int NLAST = N1 / R2;
+    constexpr int NW = 2 * T1 / 32;
+    constexpr int SH = N1 == 512 ? 0 : 1;
+    constexpr unsigned kBufB = N1 * kTB * 8u;
+    constexpr unsigned kTileBytes = N1 * kTB * 8u;
+    extern __shared__ unsigned char cols_t_smem[];
+    __shared__ float red[2 * NW];
+    __shared__ __align__(8) unsigned long long bars[NS];
+    // [exchange buffers: 2 * N1 * kTB, aligned to ColLayout::ALIGN][input tiles: NS * N1 * kTB]
+    constexpr uintptr_t AL = ColLayout<kTB>::ALIGN;
+    c2* raw = reinterpret_cast<c2*>((reinterpret_cast<uintptr_t>(cols_t_smem) + AL - 1) & ~(AL - 1));
+    const unsigned in0 = smem_addr(raw + 2 * N1 * kTB);
+    const int tile = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int u_begin = by * per, u_end = min(nunits, (by + 1) * per);
+    const int p = threadIdx.x & 1, j = threadIdx.x >> 1;
+    const int bcol = tile * kTB + 2 * p;
+    const ColAddr<kTB> A(raw, j, 2 * p);
+    const unsigned ld_in = in0 + 32u * (unsigned)(TILED ? (j ^ (tile & 3)) : j) + 16u * (unsigned)p;
+    const unsigned bar0 = smem_addr(bars);
+    float2 tw2[8], tw3[R2];
+    pass_twiddles<8, +1, 8>(j, tw2);
+    pass_twiddles<R2, +1, 64>(j, tw3);
+    {
+        const float invN = 1.0f / (2.0f * (float)M);
+        const float invM = 1.0f / (float)M;
+        const float2 base = cispif((float)((j % NLAST) * kN2 + bcol) * invN);
+        const float2 sbase = make_float2(base.x * invM, base.y * invM);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) tw3[r] = cmul(tw3[r], sbase);
+    }
+    const int m0 = (j % NLAST) * kN2 + bcol;
+    int pending = -1, parity = 0;
+    int un = u_begin;                                      // next unit whose tile has not been requested (thread 0)
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8u * s, 1);
+        mbar_init_fence();
+        while (un < u_end && load_desc(D + un).n_out < 0) ++un;
+        if (un < u_end) { tma_in<TILED, N1>(in0, &tmap, tile, un, kTileBytes, bar0); ++un; }
+    }
+    __syncthreads();
+    int k = 0;                                             // valid units processed so far
+    for (int u = u_begin; u < u_end; ++u) {
+        const UnitDesc d = load_desc(D + u);
+        if (d.n_out < 0) continue;
+        const int sb = k % NS;
+        if (NS == 2 && threadIdx.x == 0) {
+            // the other buffer was last read in the first pass of the previous unit: free since that unit's barriers
+            while (un < u_end && load_desc(D + un).n_out < 0) ++un;
+            if (un < u_end) { tma_in<TILED, N1>(in0 + (sb ^ 1) * kTileBytes, &tmap, tile, un, kTileBytes, bar0 + 8u * (sb ^ 1)); ++un; }
+        }
+        mbar_wait(bar0 + 8u * sb, (unsigned)((k / NS) & 1));
+        c2 va[R2 > 8 ? R2 : 8], vb[R2 > 8 ? R2 : 8];
+        {
+            const unsigned a = ld_in + sb * kTileBytes;
+            lds128<0 * 32 * T1>(a, va[0], vb[0]); lds128<1 * 32 * T1>(a, va[1], vb[1]);
+            lds128<2 * 32 * T1>(a, va[2], vb[2]); lds128<3 * 32 * T1>(a, va[3], vb[3]);
+            lds128<4 * 32 * T1>(a, va[4], vb[4]); lds128<5 * 32 * T1>(a, va[5], vb[5]);
+            lds128<6 * 32 * T1>(a, va[6], vb[6]); lds128<7 * 32 * T1>(a, va[7], vb[7]);
+        }
+        Dft2<8, +1>::run(va);
+        Dft2<8, +1>::run(vb);
+        col_store1_x2<kTB>(A, va, vb);
+        __syncthreads();
+        if (NS == 1 && threadIdx.x == 0) {
+            while (un < u_end && load_desc(D + un).n_out < 0) ++un;
+            if (un < u_end) { tma_in<TILED, N1>(in0, &tmap, tile, un, kTileBytes, bar0); ++un; }
+        }
+        if (!WRITE && pending >= 0 && threadIdx.x < 32) {
+            float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
+        }
+        ColLoad2<kTB, T1, 8>::run(A, va, vb);
+        bfly_tw<8>(va, tw2);
+        bfly_tw<8>(vb, tw2);
+        Dft2<8, +1>::run(va);
+        Dft2<8, +1>::run(vb);
+        col_store2_x2<kTB, kBufB>(A, va, vb);
+        __syncthreads();
+        float best = 0.0f;
+        if (N1 == 512 || j < NLAST) {
+            ColLoad2<kTB, 64, R2, kBufB>::run(A, va, vb);
+#pragma unroll
+            for (int r = 0; r < R2; ++r) { va[r] = cmul(va[r], tw3[r]); vb[r] = cmul(vb[r], tw3[r]); }
+            Dft2<R2, +1>::run(va);
+            Dft2<R2, +1>::run(vb);
+            const int lim0 = d.n_out - m0, lim1 = d.n_out - M - m0;      // column a valid iff 32768 r < lim; b: + 1
+            float* __restrict__ out = WRITE ? corr + (long long)u * corr_stride + m0 : nullptr;
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                float ar, ai, br, bi;
+                split(cmul(va[r], c_post[SH][0][r]), ar, ai);
+                split(cmul(vb[r], c_post[SH][1][r]), br, bi);
+                ar = fabsf(ar); ai = fabsf(ai); br = fabsf(br); bi = fabsf(bi);
+                if (WRITE) {
+                    // apd.py:494 (float32 divide); m0 is even and corr_stride a multiple of 32: 8-byte stores
+                    if (64 * kN2 * r + 1 < lim0) *reinterpret_cast<float2*>(out + 64 * kN2 * r) = make_float2(ar / d.mc, br / d.mc);
+                    else if (64 * kN2 * r < lim0) out[64 * kN2 * r] = ar / d.mc;
+                    if (64 * kN2 * r + 1 < lim1) *reinterpret_cast<float2*>(out + 64 * kN2 * r + M) = make_float2(ai / d.mc, bi / d.mc);
+                    else if (64 * kN2 * r < lim1) out[64 * kN2 * r + M] = ai / d.mc;
+                } else {
+                    if (64 * kN2 * r < lim0) best = fmaxf(best, ar);
+                    if (64 * kN2 * r < lim1) best = fmaxf(best, ai);
+                    if (64 * kN2 * r + 1 < lim0) best = fmaxf(best, br);
+                    if (64 * kN2 * r + 1 < lim1) best = fmaxf(best, bi);
+                }
+            }
+        }
+        if (!WRITE) {
+            best = warp_max(best);
+            if ((threadIdx.x & 31) == 0) red[parity * NW + (threadIdx.x >> 5)] = best;
+            pending = d.max_idx;
+            parity ^= 1;
+        }
+        ++k;
+    }
+    if (!WRITE) {
+        __syncthreads();
+        if (pending >= 0 && threadIdx.x < 32) {
+            float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
+        }
+    }
+}
+
 // ---------------------------------------------------------------- fused persistent kernel
 // Phase 1 (max only) as ONE persistent launch in which the four-step intermediate W never leaves L2.
 // Units are taken in groups of U; a group's row pass (128 items: 4 or 5 rows each) and column pass (128 items: 4
@@ -737,6 +1028,120 @@ long long corr_inv_dense_units(int ns, int nb)
     return (long long)((ns + tc - 1) / tc) * ((nb + tk - 1) / tk) * tc * tk;
 }
 
+// ---- tiled path: tensor maps over the intermediate, one per (buffer, shape) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static const CUtensorMap* w_tensor_map(float2* scratch, int N1, bool tiled)
+{
+    static std::map<std::pair<void*, int>, CUtensorMap> cache;
+    static EncodeTiledFn encode = nullptr;
+    const auto key = std::make_pair((void*)scratch, tiled ? N1 : -N1);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    // rows of kWBlock 8-byte elements (one block of four matrix rows); N1 / 4 of them per unit
+    const cuuint64_t dims[2] = {(cuuint64_t)kWBlock, (cuuint64_t)(N1 / 4) * 65536ull};
+    const cuuint64_t strides[1] = {(cuuint64_t)kWBlock * 8ull};
+    const cuuint32_t box[2] = {16u, (cuuint32_t)(N1 / 4)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUtensorMap m;
+    if (!tiled) {
+        // plain [c][b] layout seen as [8 * units][N1 / 8][512]: row c = j + (N1 / 8) r is element (., j, r)
+        const cuuint64_t d3[3] = {512ull, (cuuint64_t)(N1 / 8), 8ull * 65536ull};
+        const cuuint64_t s3[2] = {512ull * 8ull, (cuuint64_t)(N1 / 8) * 512ull * 8ull};
+        const cuuint32_t b3[3] = {4u, (cuuint32_t)(N1 / 8), 8u};
+        const cuuint32_t e3[3] = {1u, 1u, 1u};
+        if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, scratch, d3, s3, b3, e3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return nullptr;
+        return &cache.emplace(key, m).first->second;
+    }
+    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return nullptr;
+    return &cache.emplace(key, m).first->second;
+}
+
+template <class S, bool WRITE, int NS, bool TILED>
+static void launch_cols_t(const CUtensorMap& map, const UnitDesc* D, int nunits, int per, int M, const InvOut& out, dim3 grid,
+                          int swap, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)(2 + NS) * S::N * kTB * sizeof(c2) + ColLayout<kTB>::ALIGN;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_corr_cols_t<S, WRITE, NS, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    k_corr_cols_t<S, WRITE, NS, TILED><<<grid, 2 * (S::N / 8), smem, st>>>(map, D, nunits, per, M, out.unit_max_bits, out.corr,
+                                                                    out.corr_stride, swap);
+}
+
+static void upload_post_constants()
+{
+    static bool uploaded = false;
+    if (uploaded) return;
+    float2 h[2][2][10];
+    const int r2[2] = {8, 10};
+    const double n[2] = {2.0 * 512 * 512, 2.0 * 640 * 512};
+    for (int sh = 0; sh < 2; ++sh)
+        for (int col = 0; col < 2; ++col)
+            for (int r = 0; r < 10; ++r) {
+                const double a = M_PI * ((double)r / (2.0 * r2[sh]) + (double)col / n[sh]);
+                h[sh][col][r] = make_float2((float)cos(a), (float)sin(a));
+            }
+    cudaMemcpyToSymbol(c_post, h, sizeof(h));
+    uploaded = true;
+}
+
+static void launch_tiled(const Fft4Plan& P, const UnitDesc* D, int nunits, float2* scratch, const InvOut& out, bool write,
+                         cudaStream_t st)
+{
+    static const int per_max = std::max(1, env_int2("APD_B200_PER", 16));
+    static const int keep_h = env_int2("APD_B200_KEEP_H", 0);
+    static const int swap = env_int2("APD_B200_SWAP", 1);
+    static const int ns2 = env_int2("APD_B200_COLS_NS", 1) == 2;
+    static const int tiled_w = env_int2("APD_B200_TILED", 1) == 2;     // 2: tiled intermediate; 1: plain layout, 32-byte pieces
+    const CUtensorMap* map = w_tensor_map(scratch, P.N1, tiled_w);
+    if (!map) { fprintf(stderr, "apd_b200: cuTensorMapEncodeTiled failed\n"); abort(); }
+    upload_post_constants();
+    int per = per_max;
+    while (per > 1 && (long long)((nunits + per - 1) / per) * 64 < 148 * 8) per >>= 1;
+    const int ny = (nunits + per - 1) / per;
+    const int row_tiles = P.N1 / kRowsPerCta, col_tiles = kN2 / kTB;
+    const dim3 gr = swap ? dim3(ny, row_tiles) : dim3(row_tiles, ny);
+    const dim3 gc = swap ? dim3(ny, col_tiles) : dim3(col_tiles, ny);
+    constexpr size_t kRowSmem = (size_t)(kRowsPerCta * 2 * kN2 + 2 * kWBlock) * sizeof(c2) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_corr_rows_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmem);
+        cudaFuncSetAttribute(k_corr_rows_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmem);
+        attr = true;
+    }
+    if (tiled_w) {
+        if (keep_h) k_corr_rows_t<true><<<gr, kRowsPerCta * 64, kRowSmem, st>>>(D, nunits, per, P.M, scratch, swap);
+        else k_corr_rows_t<false><<<gr, kRowsPerCta * 64, kRowSmem, st>>>(D, nunits, per, P.M, scratch, swap);
+    } else {
+        if (keep_h) k_corr_rows3<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
+        else k_corr_rows3<false><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
+    }
+#define APD_COLS_T(SHAPE, TL)                                                                                        \
+    do {                                                                                                             \
+        if (write) launch_cols_t<SHAPE, true, 1, TL>(*map, D, nunits, per, P.M, out, gc, swap, st);                  \
+        else if (ns2) launch_cols_t<SHAPE, false, 2, TL>(*map, D, nunits, per, P.M, out, gc, swap, st);              \
+        else launch_cols_t<SHAPE, false, 1, TL>(*map, D, nunits, per, P.M, out, gc, swap, st);                       \
+    } while (0)
+    if (P.N1 == 512) { if (tiled_w) APD_COLS_T(Shape512, true); else APD_COLS_T(Shape512, false); }
+    else { if (tiled_w) APD_COLS_T(Shape640, true); else APD_COLS_T(Shape640, false); }
+#undef APD_COLS_T
+}
+
 void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
                      int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st)
 {
@@ -771,6 +1176,11 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
             if (keep_h) k_corr_fused<Shape640, true><<<grid640, 320, 0, st>>>(D, nunits, gu, lag, slots, P.M, scratch, out.unit_max_bits, counters);
             else k_corr_fused<Shape640, false><<<grid640, 320, 0, st>>>(D, nunits, gu, lag, slots, P.M, scratch, out.unit_max_bits, counters);
         }
+        return;
+    }
+    static const int tiled = env_int2("APD_B200_TILED", 1);
+    if (tiled) {
+        launch_tiled(P, D, nunits, scratch, out, write, st);
         return;
     }
     // keep at least ~8 CTAs per SM in the grid; otherwise amortise the twiddles over up to `per` units
