@@ -56,6 +56,8 @@ PROTOTYPES: dict[str, tuple[Any, list[Any]]] = {
     "apd_stage_peaks_verify": (C.c_int, [C.c_void_p, C.c_void_p]),
     "apd_stage_unit_correlation": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32,
                                              C.POINTER(C.c_int32), C.c_void_p]),
+    "apd_verify_tone": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int32), C.c_void_p]),
     "apd_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "apd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "apd_pcm_to_float": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),

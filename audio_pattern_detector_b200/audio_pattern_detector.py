@@ -325,6 +325,36 @@ class AudioPatternDetector:
         _lib.check(_lib.lib().apd_unit_n_out(self._ctx, chunk, clip_index, total_samples, C.byref(n)), "unit_n_out")
         return n.value
 
+    # ------------------------------------------------------------------ single-candidate verifier (reference :642-750)
+    def tone_candidate_metrics(self, clip_name: str, audio_section: "NDArray[np.float32]", peak: int
+                               ) -> tuple[bool, tuple[tuple[float, ...], ...]]:
+        """Device marker-tone verification of one candidate of an already normalised section (apd_verify_tone):
+        (accept, ((detected_frequency, overall_band_purity, active_frame_ratio, longest_active_run,
+        active_frame_mean_purity) for the matched segment, the left flank and the right flank))."""
+        torch = _torch()
+        idx = [c.name for c in self.audio_clips].index(clip_name)
+        sec = np.ascontiguousarray(audio_section, dtype=np.float32)
+        metrics = (C.c_double * 15)()
+        accept = C.c_int32()
+        with torch.cuda.device(self._device):
+            dev = torch.from_numpy(sec).cuda()
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().apd_verify_tone(self._ctx, idx, C.c_void_p(dev.data_ptr()), sec.size, int(peak),
+                                                  metrics, C.byref(accept), st), "apd_verify_tone")
+        m = tuple(tuple(float(metrics[s * 5 + j]) for j in range(5)) for s in range(3))
+        return bool(accept.value), m
+
+    def _verify_marker_tone(self, clip_name: str, audio_section: "NDArray[np.float32]", peak: int, clip_length: int,
+                            dominant_frequency: float, sr: int, section_ts: str) -> bool:
+        """Signature of the reference's verifier (:660-668).  The clip's length, frequency and thresholds were handed
+        to the device at construction; arguments that disagree with them cannot be honoured and raise."""
+        idx = [c.name for c in self.audio_clips].index(clip_name)
+        if clip_length != self._clip_lengths[idx] or sr != self.target_sample_rate:
+            raise ValueError("_verify_marker_tone: clip_length / sr differ from the detector's clip")
+        if not math.isclose(float(dominant_frequency), self._tone_frequencies.get(clip_name, float("nan")), rel_tol=1e-12):
+            raise ValueError("_verify_marker_tone: dominant_frequency differs from the detector's clip")
+        return self.tone_candidate_metrics(clip_name, audio_section, peak)[0]
+
     # ------------------------------------------------------------------ timestamps
     def _timestamps(self, rec: "NDArray[Any]") -> "NDArray[np.float64]":
         """reference :585 then :440-451, same order of float64 operations, for a whole candidate table."""

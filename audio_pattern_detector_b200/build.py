@@ -48,8 +48,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             sys.stderr.write(out.decode())
     if relink or not os.path.exists(LIB):
-        subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-                        "-Xcompiler", "-fPIC"], check=True)
+        # -cudart shared: the library binds to the libcudart.so.12 of the image instead of carrying a private static copy
+        subprocess.run([nvcc, "-shared", "-cudart", "shared", "-o", LIB, *objs, "-gencode",
+                        "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"], check=True)
     return LIB
 
 

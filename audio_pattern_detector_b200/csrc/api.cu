@@ -1287,6 +1287,43 @@ extern "C" int apd_stage_unit_correlation(apd_ctx* c, int32_t chunk, int32_t cli
     return APD_OK;
 }
 
+// Marker-tone verification of ONE candidate of an arbitrary, already normalised section (reference
+// audio_pattern_detector.py:660-750, _verify_marker_tone(audio_section, peak, ...)): the section is treated as chunk 0
+// of a stream of its own with unit gain, the candidate becomes the only tone work item, and the device kernels of a
+// scan compute the 3 x 5 metrics and the accept decision.  For the reference's verifier tests and known answers.
+extern "C" int apd_verify_tone(apd_ctx* c, int32_t clip, const float* section_dev, int32_t n, int32_t peak,
+                               double* metrics15_host, int32_t* accept, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!c || clip < 0 || clip >= c->n_clips || !section_dev || n <= 0 || !metrics15_host || !accept)
+        return fail(APD_ERR_INVALID, "verify_tone: bad arguments");
+    if (c->tone_ctas <= 0 || c->clips[clip].strategy != APD_STRATEGY_MARKER_TONE || !(c->clips[clip].tone_hz > 0.0))
+        return fail(APD_ERR_INVALID, "verify_tone: not a marker-tone clip");
+    if (n > c->C) return fail(APD_ERR_INVALID, "verify_tone: section longer than a chunk");
+    use_set(c, 0);
+    int rc = stage_begin(c, section_dev, 0, n, 0, 1, st);
+    if (rc) return rc;
+    const int G = (int)c->groups.size(), S = (int)c->shapes.size();
+    std::vector<double> ones((size_t)G, 1.0);
+    CK(cudaMemcpyAsync(c->d_gain, ones.data(), sizeof(double) * G, cudaMemcpyHostToDevice, st));
+    struct { int ci, clip, peak; float height; } item = {0, clip, peak, 1.0f};
+    static_assert(sizeof(item) == 16, "ToneItem layout");
+    if (tone_item_bytes() != sizeof(item)) return fail(APD_ERR_INVALID, "verify_tone: work item layout");
+    CK(cudaMemcpyAsync(c->d_tone_items, &item, sizeof(item), cudaMemcpyHostToDevice, st));
+    const int one = 1;
+    CK(cudaMemcpyAsync(c->d_counts + S + 3, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    phase2_tone(c, 1, st);
+    apd_candidate rec;
+    CK(cudaMemcpyAsync(&rec, c->d_out, sizeof(rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    c->staged = false;
+    for (int sgm = 0; sgm < 3; ++sgm)
+        for (int j = 0; j < 5; ++j) metrics15_host[sgm * 5 + j] = rec.tone[sgm][j];
+    *accept = (rec.flags & APD_FLAG_ACCEPT) ? 1 : 0;
+    return APD_OK;
+}
+
 extern "C" int64_t apd_launch_count(apd_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" int apd_profile(apd_ctx* c, int enable)

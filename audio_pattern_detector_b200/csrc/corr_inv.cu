@@ -82,6 +82,8 @@ __device__ __forceinline__ UnitDesc load_desc(const UnitDesc* p)
     return d;
 }
 
+__device__ int g_walias = 0;       // timing experiment only (APD_B200_WALIAS): units share W slots, results invalid
+
 constexpr int kN2 = 512;          // row length (complex)
 constexpr int kRowsPerCta = 4;    // 64 threads per row
 
@@ -215,7 +217,8 @@ __device__ __forceinline__ void rows_item(c2* buf, const UnitDesc* __restrict__ 
         APD_ROW_LOAD8(A, kB, v)
         bfly_tw<8>(v, tw3);
         Dft2<8, +1>::run(v);
-        c2* __restrict__ out = reinterpret_cast<c2*>(Wg + (long long)(u - u_begin) * M + row_off);
+        const int wal = g_walias;
+        c2* __restrict__ out = reinterpret_cast<c2*>(Wg + (long long)((wal ? u % wal : u) - u_begin) * M + row_off);
 #pragma unroll
         for (int r = 0; r < 8; ++r) out[64 * r] = cmul(v[r], fs[r]);
     }
@@ -690,8 +693,17 @@ __device__ __forceinline__ void tma_load_tile3(unsigned dst, const CUtensorMap* 
 template <bool TILED, int N1>
 __device__ __forceinline__ void tma_in(unsigned dst, const CUtensorMap* map, int tile, int u, unsigned bytes, unsigned bar)
 {
+    const int wal = g_walias;
+    if (wal) u %= wal;
     if (TILED) tma_load_tile(dst, map, tile * 16, u * (N1 / 4), bytes, bar);
     else tma_load_tile3(dst, map, tile * 4, 0, u * 8, bytes, bar);
+}
+
+// best = max(best, y) if a < b (one ISETP + one predicated FMNMX; y >= 0)
+__device__ __forceinline__ float max_if_lt(float best, float y, int a, int b)
+{
+    asm("{\n.reg .pred p;\nsetp.lt.s32 p, %2, %3;\n@p max.f32 %0, %0, %1;\n}" : "+f"(best) : "f"(y), "r"(a), "r"(b));
+    return best;
 }
 
 // Row pass, tiled output.  Same passes as rows_item; the last pass writes to a double-buffered staging area.
@@ -792,7 +804,7 @@ k_corr_rows_t(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2
 // tile is requested after the first exchange (its latency is covered by two passes); with two, a whole unit ahead.
 // WRITE: normalised correlation written out (phase 2) with the arithmetic of the maximum (phase 1), so that the
 // phase-2 values divided by max(self max, phase-1 max) reproduce that maximum bit for bit.
-template <class S, bool WRITE, int NS, bool TILED>
+template <class S, bool WRITE, int NS, bool TILED, int EPI = 1>
 __global__ void __launch_bounds__(2 * (S::N / 8), WRITE ? 2 : (S::N == 512 ? 4 : 3))
 k_corr_cols_t(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict__ D, int nunits, int per, int M,
               unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride, int swap)
@@ -888,6 +900,7 @@ k_corr_cols_t(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restri
             Dft2<R2, +1>::run(va);
             Dft2<R2, +1>::run(vb);
             const int lim0 = d.n_out - m0, lim1 = d.n_out - M - m0;      // column a valid iff 32768 r < lim; b: + 1
+            const bool all_re = d.n_out >= M;                            // unit-uniform (false only for a short last chunk)
             float* __restrict__ out = WRITE ? corr + (long long)u * corr_stride + m0 : nullptr;
 #pragma unroll
             for (int r = 0; r < R2; ++r) {
@@ -901,11 +914,21 @@ k_corr_cols_t(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restri
                     else if (64 * kN2 * r < lim0) out[64 * kN2 * r] = ar / d.mc;
                     if (64 * kN2 * r + 1 < lim1) *reinterpret_cast<float2*>(out + 64 * kN2 * r + M) = make_float2(ai / d.mc, bi / d.mc);
                     else if (64 * kN2 * r < lim1) out[64 * kN2 * r + M] = ai / d.mc;
-                } else {
+                } else if (EPI == 0) {
                     if (64 * kN2 * r < lim0) best = fmaxf(best, ar);
                     if (64 * kN2 * r < lim1) best = fmaxf(best, ai);
                     if (64 * kN2 * r + 1 < lim0) best = fmaxf(best, br);
                     if (64 * kN2 * r + 1 < lim1) best = fmaxf(best, bi);
+                } else if (all_re) {
+                    // n_out >= M: every real part is a valid output; the imaginary parts (outputs m + M) need the test
+                    best = fmaxf(best, fmaxf(ar, br));
+                    best = max_if_lt(best, ai, 64 * kN2 * r, lim1);
+                    best = max_if_lt(best, bi, 64 * kN2 * r + 1, lim1);
+                } else {
+                    best = max_if_lt(best, ar, 64 * kN2 * r, lim0);
+                    best = max_if_lt(best, ai, 64 * kN2 * r, lim1);
+                    best = max_if_lt(best, br, 64 * kN2 * r + 1, lim0);
+                    best = max_if_lt(best, bi, 64 * kN2 * r + 1, lim1);
                 }
             }
         }
@@ -924,6 +947,123 @@ k_corr_cols_t(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restri
             t = warp_max(t);
             if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
         }
+    }
+}
+
+// Column pass, one column per thread (4 x N1/8 threads, twice the warps of the two-column kernel for the same
+// shared memory): the pass is bound by latency (barriers, shared-memory round trips), not by issue slots.  The last
+// pass's twiddles are rebuilt per unit from two registers (w and the folded post-twiddle base) to stay under 68
+// registers (three 320-thread CTAs per SM).
+template <class S, int MINB>
+__global__ void __launch_bounds__(kTB * (S::N / 8), MINB)
+k_corr_cols_u(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict__ D, int nunits, int per, int M,
+              unsigned int* __restrict__ unit_max_bits, int swap)
+{
+    constexpr int N1 = S::N;
+    constexpr int T1 = N1 / 8;
+    constexpr int R2 = S::R2;
+    constexpr int NLAST = N1 / R2;
+    constexpr int NW = kTB * T1 / 32;
+    constexpr unsigned kBufB = N1 * kTB * 8u;
+    constexpr unsigned kTileBytes = N1 * kTB * 8u;
+    extern __shared__ unsigned char cols_u_smem[];
+    __shared__ float red[2 * NW];
+    __shared__ __align__(8) unsigned long long bars[1];
+    constexpr uintptr_t AL = ColLayout<kTB>::ALIGN;
+    c2* raw = reinterpret_cast<c2*>((reinterpret_cast<uintptr_t>(cols_u_smem) + AL - 1) & ~(AL - 1));
+    const unsigned in0 = smem_addr(raw + 2 * N1 * kTB);
+    const int tile = swap ? blockIdx.y : blockIdx.x, by = swap ? blockIdx.x : blockIdx.y;
+    const int u_begin = by * per, u_end = min(nunits, (by + 1) * per);
+    const int q = threadIdx.x % kTB, j = threadIdx.x / kTB;
+    const int bcol = tile * kTB + q;
+    const ColAddr<kTB> A(raw, j, q);
+    const unsigned ld_in = in0 + 32u * (unsigned)j + 8u * (unsigned)q;
+    const unsigned bar0 = smem_addr(bars);
+    float2 tw2[8];
+    pass_twiddles<8, +1, 8>(j, tw2);
+    // last pass: tw3[r] = w^r * sbase, w = e^{2 pi i (j mod 64) / (64 R2)}, sbase = e^{i pi m0 / N} / M
+    const float2 w3 = cispif(2.0f * (float)(j % 64) * (1.0f / (float)(64 * R2)));
+    float2 sbase;
+    {
+        const float invN = 1.0f / (2.0f * (float)M);
+        const float invM = 1.0f / (float)M;
+        const float2 base = cispif((float)((j % NLAST) * kN2 + bcol) * invN);
+        sbase = make_float2(base.x * invM, base.y * invM);
+    }
+    const int m0 = (j % NLAST) * kN2 + bcol;
+    int pending = -1, parity = 0;
+    int un = u_begin;
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init_fence();
+        while (un < u_end && load_desc(D + un).n_out < 0) ++un;
+        if (un < u_end) { tma_in<false, N1>(in0, &tmap, tile, un, kTileBytes, bar0); ++un; }
+    }
+    __syncthreads();
+    int k = 0;
+    for (int u = u_begin; u < u_end; ++u) {
+        const UnitDesc d = load_desc(D + u);
+        if (d.n_out < 0) continue;
+        mbar_wait(bar0, (unsigned)(k & 1));
+        c2 v[R2 > 8 ? R2 : 8];
+        v[0] = lds<0 * 32 * T1>(ld_in); v[1] = lds<1 * 32 * T1>(ld_in); v[2] = lds<2 * 32 * T1>(ld_in);
+        v[3] = lds<3 * 32 * T1>(ld_in); v[4] = lds<4 * 32 * T1>(ld_in); v[5] = lds<5 * 32 * T1>(ld_in);
+        v[6] = lds<6 * 32 * T1>(ld_in); v[7] = lds<7 * 32 * T1>(ld_in);
+        Dft2<8, +1>::run(v);
+        col_store1<kTB>(A, v);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            while (un < u_end && load_desc(D + un).n_out < 0) ++un;
+            if (un < u_end) { tma_in<false, N1>(in0, &tmap, tile, un, kTileBytes, bar0); ++un; }
+        }
+        if (pending >= 0 && threadIdx.x < 32) {
+            float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
+        }
+        ColLoad<kTB, T1, 8>::run(A, v);
+        bfly_tw<8>(v, tw2);
+        Dft2<8, +1>::run(v);
+        col_store2<kTB, kBufB>(A, v);
+        __syncthreads();
+        float best = 0.0f;
+        if (N1 == 512 || j < NLAST) {
+            ColLoad<kTB, 64, R2, kBufB>::run(A, v);
+            {
+                c2 t = from_f2(sbase);
+                const c2 w = from_f2(w3);
+#pragma unroll
+                for (int r = 0; r < R2; ++r) {
+                    v[r] = cmul(v[r], t);
+                    if (r + 1 < R2) t = cmul(t, w);
+                }
+            }
+            Dft2<R2, +1>::run(v);
+            const int lim1 = d.n_out - M - m0;
+            const int lim0 = d.n_out - m0;
+            const bool all_re = d.n_out >= M;
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                const float2 pc = R2 == 8 ? post_const8(r < 8 ? r : 0) : post_const10(r);
+                float zr, zi;
+                split(r == 0 ? v[0] : cmul(v[r], pc.x, pc.y), zr, zi);
+                zr = fabsf(zr); zi = fabsf(zi);
+                if (all_re) best = fmaxf(best, zr);
+                else best = max_if_lt(best, zr, 64 * kN2 * r, lim0);
+                best = max_if_lt(best, zi, 64 * kN2 * r, lim1);
+            }
+        }
+        best = warp_max(best);
+        if ((threadIdx.x & 31) == 0) red[parity * NW + (threadIdx.x >> 5)] = best;
+        pending = d.max_idx;
+        parity ^= 1;
+        ++k;
+    }
+    __syncthreads();
+    if (pending >= 0 && threadIdx.x < 32) {
+        float t = threadIdx.x < NW ? red[(parity ^ 1) * NW + threadIdx.x] : 0.0f;
+        t = warp_max(t);
+        if (threadIdx.x == 0) atomicMax(unit_max_bits + pending, __float_as_uint(t));
     }
 }
 
@@ -1069,17 +1209,17 @@ static const CUtensorMap* w_tensor_map(float2* scratch, int N1, bool tiled)
     return &cache.emplace(key, m).first->second;
 }
 
-template <class S, bool WRITE, int NS, bool TILED>
+template <class S, bool WRITE, int NS, bool TILED, int EPI = 1>
 static void launch_cols_t(const CUtensorMap& map, const UnitDesc* D, int nunits, int per, int M, const InvOut& out, dim3 grid,
                           int swap, cudaStream_t st)
 {
     constexpr size_t smem = (size_t)(2 + NS) * S::N * kTB * sizeof(c2) + ColLayout<kTB>::ALIGN;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_corr_cols_t<S, WRITE, NS, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_corr_cols_t<S, WRITE, NS, TILED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    k_corr_cols_t<S, WRITE, NS, TILED><<<grid, 2 * (S::N / 8), smem, st>>>(map, D, nunits, per, M, out.unit_max_bits, out.corr,
+    k_corr_cols_t<S, WRITE, NS, TILED, EPI><<<grid, 2 * (S::N / 8), smem, st>>>(map, D, nunits, per, M, out.unit_max_bits, out.corr,
                                                                     out.corr_stride, swap);
 }
 
@@ -1104,13 +1244,20 @@ static void launch_tiled(const Fft4Plan& P, const UnitDesc* D, int nunits, float
                          cudaStream_t st)
 {
     static const int per_max = std::max(1, env_int2("APD_B200_PER", 16));
-    static const int keep_h = env_int2("APD_B200_KEEP_H", 0);
+    static const int keep_h = env_int2("APD_B200_KEEP_H", 1);
     static const int swap = env_int2("APD_B200_SWAP", 1);
     static const int ns2 = env_int2("APD_B200_COLS_NS", 1) == 2;
+    static const int epi0 = env_int2("APD_B200_EPI", 1) == 0;
     static const int tiled_w = env_int2("APD_B200_TILED", 1) == 2;     // 2: tiled intermediate; 1: plain layout, 32-byte pieces
     const CUtensorMap* map = w_tensor_map(scratch, P.N1, tiled_w);
     if (!map) { fprintf(stderr, "apd_b200: cuTensorMapEncodeTiled failed\n"); abort(); }
     upload_post_constants();
+    static bool wal_set = false;
+    if (!wal_set) {
+        const int wal = env_int2("APD_B200_WALIAS", 0);
+        if (wal > 0) cudaMemcpyToSymbol(g_walias, &wal, sizeof(int));
+        wal_set = true;
+    }
     int per = per_max;
     while (per > 1 && (long long)((nunits + per - 1) / per) * 64 < 148 * 8) per >>= 1;
     const int ny = (nunits + per - 1) / per;
@@ -1131,10 +1278,32 @@ static void launch_tiled(const Fft4Plan& P, const UnitDesc* D, int nunits, float
         if (keep_h) k_corr_rows3<true><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
         else k_corr_rows3<false><<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch, swap);
     }
+    static const int cols_u = env_int2("APD_B200_COLS_U", 0);
+    if (cols_u && !write && !tiled_w) {
+        constexpr size_t sm512 = (size_t)3 * 512 * kTB * sizeof(c2) + ColLayout<kTB>::ALIGN;
+        constexpr size_t sm640 = (size_t)3 * 640 * kTB * sizeof(c2) + ColLayout<kTB>::ALIGN;
+        static bool attr_u = false;
+        if (!attr_u) {
+            cudaFuncSetAttribute(k_corr_cols_u<Shape512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm512);
+            cudaFuncSetAttribute(k_corr_cols_u<Shape640, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm640);
+            cudaFuncSetAttribute(k_corr_cols_u<Shape512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm512);
+            cudaFuncSetAttribute(k_corr_cols_u<Shape640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm640);
+            attr_u = true;
+        }
+        if (P.N1 == 512) {
+            if (cols_u == 3) k_corr_cols_u<Shape512, 3><<<gc, kTB * 64, sm512, st>>>(*map, D, nunits, per, P.M, out.unit_max_bits, swap);
+            else k_corr_cols_u<Shape512, 2><<<gc, kTB * 64, sm512, st>>>(*map, D, nunits, per, P.M, out.unit_max_bits, swap);
+        } else {
+            if (cols_u == 3) k_corr_cols_u<Shape640, 3><<<gc, kTB * 80, sm640, st>>>(*map, D, nunits, per, P.M, out.unit_max_bits, swap);
+            else k_corr_cols_u<Shape640, 2><<<gc, kTB * 80, sm640, st>>>(*map, D, nunits, per, P.M, out.unit_max_bits, swap);
+        }
+        return;
+    }
 #define APD_COLS_T(SHAPE, TL)                                                                                        \
     do {                                                                                                             \
         if (write) launch_cols_t<SHAPE, true, 1, TL>(*map, D, nunits, per, P.M, out, gc, swap, st);                  \
         else if (ns2) launch_cols_t<SHAPE, false, 2, TL>(*map, D, nunits, per, P.M, out, gc, swap, st);              \
+        else if (epi0) launch_cols_t<SHAPE, false, 1, TL, 0>(*map, D, nunits, per, P.M, out, gc, swap, st);          \
         else launch_cols_t<SHAPE, false, 1, TL>(*map, D, nunits, per, P.M, out, gc, swap, st);                       \
     } while (0)
     if (P.N1 == 512) { if (tiled_w) APD_COLS_T(Shape512, true); else APD_COLS_T(Shape512, false); }

@@ -136,6 +136,13 @@ APD_API int apd_stage_peaks_verify(apd_ctx* ctx, void* cuda_stream);
 /* Full normalised correlation of one unit of the staged batch, to host (n_out floats). */
 APD_API int apd_stage_unit_correlation(apd_ctx* ctx, int32_t chunk, int32_t clip, float* out_host, int32_t capacity,
                                int32_t* n_out, void* cuda_stream);
+/* Marker-tone verification of one candidate `peak` (index into the 'full' correlation, i.e. match start = peak - L + 1)
+ * of an already normalised section in device memory (n <= chunk_samples): the three segment metrics (match, left flank,
+ * right flank) x (detected frequency, band purity, active frame ratio, longest active run, mean active purity) and
+ * the accept decision.  Replaces AudioPatternDetector._verify_marker_tone (reference audio_pattern_detector.py:660-750,
+ * detection_utils.py:41-142) for callers that verify a single candidate (tests/test_marker_tone_verification.py:66). */
+APD_API int apd_verify_tone(apd_ctx* ctx, int32_t clip, const float* section_dev, int32_t n_samples, int32_t peak,
+                            double* metrics15_host, int32_t* accept, void* cuda_stream);
 
 /* Stage timing: when enabled, apd_scan brackets its four stages with CUDA events on the caller's
  * stream and accumulates their device times (ms): [0] loudness, [1] forward FFT,

@@ -19,10 +19,13 @@ SYN_RUNS = load_json("synthetic_runs.json")
 def test_fixtures_match_oracle_and_reference_golden(run):
     clips, audio = fixture_clips(run), fixture_audio(run)
     out = compare_with_oracle(clips, audio, run["sr"], run.get("requested_spc", 60))
-    if out["tie_units"] == 0:
-        # and the unmodified reference's own result on this fixture (tests/golden/fixture_runs.json)
-        assert out["result"].peak_times == run["timestamps"]
-        assert [[n, t] for t, n in out["result"].events] == run["events"]
+    print(f"tie_units={out['tie_units']} of {out['units']} units")
+    # no real fixture has rounding-level ties between competing peaks (checked against the float64 oracle on the
+    # CPU): the tie allowance of golden_util.peaks_match must never be what makes a fixture pass
+    assert out["tie_units"] == 0
+    # and the unmodified reference's own result on this fixture (tests/golden/fixture_runs.json)
+    assert out["result"].peak_times == run["timestamps"]
+    assert [[n, t] for t, n in out["result"].events] == run["events"]
 
 
 @pytest.mark.parametrize("run", SYN_RUNS, ids=lambda r: r["case"]["id"])
@@ -30,6 +33,11 @@ def test_synthetic_streams_match_oracle(run):
     clips, audio = synthetic_inputs(run)
     case = run["case"]
     out = compare_with_oracle(clips, audio, case["sr"], case["spc"], case.get("height_min"), max_batch_chunks=4)
+    print(f"tie_units={out['tie_units']} of {out['units']} units")
+    # only the exactly periodic tone-in-silence cases (beeps_*) have float32 ties between neighbouring maxima of the
+    # same height; every other stream must match peak for peak
+    if not case["id"].startswith("beeps_"):
+        assert out["tie_units"] == 0
     if out["tie_units"] == 0:
         assert out["result"].peak_times == run["timestamps"]
 
@@ -253,3 +261,61 @@ def test_two_pass_row_kernel_variant_matches():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_tone_known_answer_signals_on_device():
+    """The reference's verifier known answers (tests/test_marker_tone_verification.py:77-95: clean tone accepted,
+    harmonic stack and 920 -> 1160 Hz sweep rejected), through the device tone verifier (apd_verify_tone) and the
+    reference-named shim; metrics within 1e-4 of the values recorded from the unmodified reference
+    (tests/golden/tone_kat.json)."""
+    kat = load_json("tone_kat.json")
+    run = [r for r in FIXTURE_RUNS if r["wav"] == "rthk_section_with_beep.wav" and r["sr"] == 8000][0]
+    clips = [c for c in fixture_clips(run) if c["name"] == "rthk_beep"]
+    assert clips and clips[0]["strategy"] == "marker_tone"
+    det = make_detector(clips, 8000, 60)
+    L = len(clips[0]["audio"])
+    accepts = []
+    names = ("detected_frequency", "overall_band_purity", "active_frame_ratio", "longest_active_run",
+             "active_frame_mean_purity")
+    for name, sig in kat["signals"].items():
+        x = np.array(sig["samples"], dtype=np.float32)
+        assert x.size == L
+        ok, m = det.tone_candidate_metrics("rthk_beep", x, L - 1)
+        for nm, got in zip(names, m[0]):
+            want = sig["metrics"][nm]
+            assert abs(got - want) <= 1e-4 * max(abs(want), 1e-2), (name, nm, got, want)
+        assert ok == sig["accept"], name
+        accepts.append(det._verify_marker_tone(clip_name="rthk_beep", audio_section=x, peak=L - 1, clip_length=L,
+                                               dominant_frequency=kat["f0"], sr=8000, section_ts="00:00:00"))
+    assert accepts == [True, False, False]
+
+
+def test_phase2_normalised_maximum_is_exactly_one():
+    """Phase 2 re-computes a selected unit's correlation with the arithmetic that produced its phase-1 maximum, so the
+    normalised correlation (apd.py:492-494) peaks at exactly 1.0f whenever the unit's maximum is the divisor."""
+    import ctypes as C
+    import torch
+    from audio_pattern_detector_b200 import _lib
+    run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c60"][0]
+    clips, audio = synthetic_inputs(run)
+    det = make_detector(clips, 8000, 60, max_batch_chunks=4)
+    res = det.scan_array(audio, collect_trace=True)
+    dev = torch.from_numpy(audio).cuda()
+    L_ = _lib.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n_chunks = (audio.size + det._chunk_samples - 1) // det._chunk_samples
+    checked = 0
+    _lib.check(L_.apd_stage_loudness(det._ctx, C.c_void_p(dev.data_ptr()), 0, audio.size, 0, min(4, n_chunks), st), "stage")
+    _lib.check(L_.apd_stage_forward_fft(det._ctx, st), "stage")
+    _lib.check(L_.apd_stage_correlate_max(det._ctx, st), "stage")
+    buf = np.empty(det._chunk_samples + det._max_halo + max(det._clip_lengths), dtype=np.float32)
+    for (ci, name), tr in res.unit_trace.items():
+        if ci >= min(4, n_chunks) or not tr["absmax"] >= tr["max_choose"] or tr["absmax"] <= 0:
+            continue
+        idx = [c["name"] for c in clips].index(name)
+        n = C.c_int32()
+        _lib.check(L_.apd_stage_unit_correlation(det._ctx, ci, idx, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size,
+                                                 C.byref(n), st), "unit_correlation")
+        assert float(buf[:n.value].max()) == 1.0, (ci, name, float(buf[:n.value].max()))
+        checked += 1
+    assert checked > 0
