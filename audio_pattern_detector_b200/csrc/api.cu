@@ -185,11 +185,6 @@ struct apd_ctx {
     KwConfig kw{};
     std::map<int, Fft4Plan> self_plans;
     long long launches = 0;
-    // opt-in (APD_B200_L2_PERSIST=1): the four-step intermediates of the two correlate streams are marked
-    // persisting in L2 (access-policy windows), so that with a small inv_units they never travel to HBM
-    bool l2_persist = false;
-    size_t l2_window_bytes = 0;           // bytes of each intermediate covered by its window
-    float l2_hit_ratio = 1.0f;
 
     // per-clip device tables
     int *d_clip_len = nullptr, *d_clip_group = nullptr, *d_strategy = nullptr, *d_is_short = nullptr;
@@ -674,11 +669,6 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     if (const char* e = getenv("APD_B200_SLOTS")) c->n_slots = std::min(std::max(8, atoi(e)), (int)kMaxSlots);
     c->inv_units = 512;
     if (const char* e = getenv("APD_B200_INV_UNITS")) c->inv_units = std::max(1, atoi(e));
-    {
-        int tc = 0, tk = 0;
-        corr_inv_tiling(&tc, &tk);
-        if (tc > 0) c->inv_units = (c->inv_units + tc * tk - 1) / (tc * tk) * (tc * tk);
-    }
     c->scratch_elems = std::max<long long>((long long)B * (long long)max_class_groups, c->inv_units) * max_M;
     CK(dalloc(&c->d_scratch, (size_t)c->scratch_elems));
     c->d_scratch_fwd = c->d_scratch;
@@ -693,21 +683,6 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(cudaMalloc(&c->d_unit_desc_b, corr_inv_desc_bytes(c->inv_units)));
     CK(dalloc(&c->d_scratch2, (size_t)c->n_slots * max_M));
     CK(cudaMalloc(&c->d_unit_desc2, corr_inv_desc_bytes(c->n_slots)));
-    if (const char* e = getenv("APD_B200_L2_PERSIST")) if (atoi(e)) {
-        int max_persist = 0, max_window = 0;
-        CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device));
-        CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device));
-        if (max_persist > 0 && max_window > 0) {
-            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
-            const size_t want = (size_t)c->inv_units * (size_t)max_M * sizeof(float2);
-            c->l2_window_bytes = std::min(want, (size_t)max_window);
-            c->l2_hit_ratio = (float)std::min(1.0, (double)max_persist / (2.0 * (double)c->l2_window_bytes));
-            c->l2_persist = true;
-            if (getenv("APD_B200_VERBOSE"))
-                fprintf(stderr, "apd_b200: L2 persisting max %d B, window max %d B, intermediate %zu B x 2, hit ratio %.2f\n",
-                        max_persist, max_window, want, c->l2_hit_ratio);
-        }
-    }
     c->sel_capacity = B * n_clips;
     for (auto& b : used_sets(c)) {
         CK(dalloc(&b.d_unit_max, (size_t)B * n_clips));
@@ -933,41 +908,25 @@ static int stage_correlate_max(apd_ctx* c, cudaStream_t st)
         CK(cudaEventRecord(c->corr_fork, st));
         CK(cudaStreamWaitEvent(c->corr2, c->corr_fork, 0));
     }
-    if (c->l2_persist) {
-        cudaStreamAttrValue a{};
-        a.accessPolicyWindow.num_bytes = c->l2_window_bytes;
-        a.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
-        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        a.accessPolicyWindow.base_ptr = c->d_scratch;
-        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a));
-        a.accessPolicyWindow.base_ptr = c->d_scratch_b;
-        CK(cudaStreamSetAttribute(c->corr2, cudaStreamAttributeAccessPolicyWindow, &a));
-    }
     int launch = 0;
     for (auto& sc : c->shapes) {
         const int ns = (int)sc.clips.size();
-        int tc = 0, tk = 0;
-        if (corr_inv_supported(sc.plan) && clip_major) corr_inv_tiling(&tc, &tk);
-        // unit positions of the launch sequence (with unit tiling some positions of edge tiles are unused)
-        const long long nunits = tc > 0 ? corr_inv_dense_units(ns, B) : (long long)B * ns;
-        for (long long u0 = 0; u0 < nunits; u0 += c->inv_units, ++launch) {
-            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, (int)u0, clip_major ? B : 0, tc, tk};
+        const long long nunits = (long long)B * ns;
+        // launches of equal size (a multiple of 16 units) instead of full ones plus a small remainder
+        const long long nl = (nunits + c->inv_units - 1) / c->inv_units;
+        const long long step = std::min<long long>(c->inv_units, ((nunits + nl - 1) / nl + 15) / 16 * 16);
+        for (long long u0 = 0; u0 < nunits; u0 += step, ++launch) {
+            UnitSrc U{nullptr, nullptr, sc.d_clips, ns, (int)u0, clip_major ? B : 0, 0, 0};
             const bool odd = two_streams && (launch & 1);
-            launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, (int)std::min<long long>(c->inv_units, nunits - u0),
+            launch_inverse(sc.plan, X, c->d_spec, c->spec_slab, U, (int)std::min<long long>(step, nunits - u0),
                            odd ? c->d_scratch_b : c->d_scratch, odd ? c->d_unit_desc_b : c->d_unit_desc, O, false,
                            odd ? c->corr2 : st);
-            c->launches += tc > 0 ? 2 : 3;
+            c->launches += 3;
         }
     }
     if (two_streams) {
         CK(cudaEventRecord(c->corr_join, c->corr2));
         CK(cudaStreamWaitEvent(st, c->corr_join, 0));
-    }
-    if (c->l2_persist) {                  // the caller's stream goes back to normal caching for what follows
-        cudaStreamAttrValue a{};
-        a.accessPolicyWindow.num_bytes = 0;
-        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a));
     }
     CK(cudaGetLastError());
     return APD_OK;

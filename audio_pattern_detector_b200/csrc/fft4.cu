@@ -193,7 +193,7 @@ k_inv_cols(Fft4Plan P, UnitCtx C, UnitSrc U, const float2* __restrict__ W, InvOu
 // ------------------------------------------------------------------ fast kernels (hot shapes)
 // Forward transforms of the hot shapes (the inverse ones live in corr_inv.cu).
 // Row kernels handle N2 = 512 = 8*8*8 with 64 threads per row (one radix-8 butterfly per thread per
-// pass); column kernels handle N1 in {512 = 8*8*8, 640 = 8*8*10} with one thread per butterfly and
+// pass); column kernels handle N1 in {512 = 8*8*8, 576 = 8*8*9, 640 = 8*8*10} with one thread per butterfly and
 // TB adjacent columns on the lanes.  All complex arithmetic is packed (cpx2.cuh, fft_fast.cuh).
 constexpr int kRowN = 512;
 constexpr int kRowPitch = kRowN;
@@ -252,7 +252,7 @@ k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ s
 // Fused with the section load: loudness gain, clamp, NaN scrub (lib.rs:220-227, apd.py:489-490), packing
 // u[m] = x[m] - i x[m + M] and the pre-twiddle e^{-i pi m / N}.  Exchange addressing: ColAddr / ColLoad.
 template <class S, int TB>
-__global__ void __launch_bounds__(TB * (S::N / 8), (TB * (S::N / 8) <= 256) ? 3 : (TB * (S::N / 8) <= 320 ? 2 : 1))
+__global__ void __launch_bounds__(TB * (S::N / 8), TB * (S::N / 8) <= 320 ? 2 : 1)
 k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restrict__ gains, int gain_stride,
                 float2* __restrict__ T, int ntr, int per)
 {
@@ -348,15 +348,19 @@ static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G
 {
     dim3 gc(P.N2 / TB, ny);
     const size_t sm512 = (size_t)(2 * 512 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
+    const size_t sm576 = (size_t)(2 * 576 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
     const size_t sm640 = (size_t)(2 * 640 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_fwd_cols_fast<Shape512, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm512);
+        cudaFuncSetAttribute(k_fwd_cols_fast<Shape576, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm576);
         cudaFuncSetAttribute(k_fwd_cols_fast<Shape640, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm640);
         attr = true;
     }
     if (fs == 512)
         k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, sm512, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
+    else if (fs == 576)
+        k_fwd_cols_fast<Shape576, TB><<<gc, TB * 72, sm576, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
     else
         k_fwd_cols_fast<Shape640, TB><<<gc, TB * 80, sm640, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
 }
@@ -365,6 +369,7 @@ static int fast_shape(const Fft4Plan& P)
 {
     if (P.N2 != kRowN) return 0;
     if (P.N1 == 512) return 512;
+    if (P.N1 == 576) return 576;
     if (P.N1 == 640) return 640;
     return 0;
 }
@@ -426,7 +431,7 @@ bool build_plan(int M_min, Fft4Plan* plan, std::string* err)
             if (M < M_min) continue;
             const double skew = std::fabs(std::log2((double)n1 / (double)n2));
             double cost = (double)M * (1.0 + 0.03 * skew);
-            if (n2 == kRowN && (n1 == 512 || n1 == 640)) cost *= 0.6;      // register-resident fast kernels exist
+            if (n2 == kRowN && (n1 == 512 || n1 == 576 || n1 == 640)) cost *= 0.6;      // register-resident fast kernels exist
             if (cost < best_cost) { best_cost = cost; bN1 = n1; bN2 = n2; }
         }
     if (!bN1) {

@@ -80,6 +80,45 @@ template <int SIGN> struct Dft2<5, SIGN> {
     }
 };
 
+template <int SIGN> struct Dft2<3, SIGN> {
+    static __device__ __forceinline__ void run(c2* v)
+    {
+        const float s3 = 0.86602540378443864676f;           // sin(2pi/3)
+        const c2 t = v[1] + v[2];
+        const c2 u = axpy(v[0], -0.5f, t);
+        const c2 d = rot<SIGN>(mul2(v[1] - v[2], mk(s3, s3)));
+        v[0] = v[0] + t;
+        v[1] = u + d;
+        v[2] = u - d;
+    }
+};
+
+// 9 = 3 x 3: DFT3 over r1 of v[3 r1 + r2], twiddles w9^{q1 r2}, DFT3 over r2 -> X[q1 + 3 q2]
+template <int SIGN> struct Dft2<9, SIGN> {
+    static __device__ __forceinline__ void run(c2* v)
+    {
+        const float c1 = 0.76604444311897803520f, s1 = 0.64278760968653932632f;     // cos, sin (2pi/9)
+        const float c2_ = 0.17364817766693034885f, s2 = 0.98480775301220805937f;    // (4pi/9)
+        const float c4 = -0.93969262078590838405f, s4 = 0.34202014332566873304f;    // (8pi/9)
+        c2 y[3][3];
+#pragma unroll
+        for (int r2 = 0; r2 < 3; ++r2) {
+            c2 t[3] = {v[r2], v[3 + r2], v[6 + r2]};
+            Dft2<3, SIGN>::run(t);
+            y[0][r2] = t[0]; y[1][r2] = t[1]; y[2][r2] = t[2];
+        }
+        y[1][1] = cmul(y[1][1], c1, SIGN * s1);
+        y[1][2] = cmul(y[1][2], c2_, SIGN * s2);
+        y[2][1] = cmul(y[2][1], c2_, SIGN * s2);
+        y[2][2] = cmul(y[2][2], c4, SIGN * s4);
+#pragma unroll
+        for (int q1 = 0; q1 < 3; ++q1) {
+            Dft2<3, SIGN>::run(y[q1]);
+            v[q1] = y[q1][0]; v[q1 + 3] = y[q1][1]; v[q1 + 6] = y[q1][2];
+        }
+    }
+};
+
 template <int SIGN> struct Dft2<10, SIGN> {
     static __device__ __forceinline__ void run(c2* v)
     {
@@ -106,6 +145,7 @@ template <int N_, int R0_, int R1_, int R2_> struct Shape3 {
     static_assert(R0_ * R1_ * R2_ == N_, "radices must multiply to N");
 };
 using Shape512 = Shape3<512, 8, 8, 8>;
+using Shape576 = Shape3<576, 8, 8, 9>;
 using Shape640 = Shape3<640, 8, 8, 10>;
 
 // powers w^0..w^(R-1) of a unit complex number (tree: depth log2 R)
@@ -231,8 +271,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 
 // Column-kernel exchange layout: TB adjacent columns on the lanes (q = tid % TB), butterfly j = tid / TB,
 // word(e, q) = TB * (e ^ ((e >> 3) & SW)) + q with SW = 3 (TB = 4) or 1 (TB = 8); N1 = 8 * 8 * R2.
-//   loads  e = j + T r (T = N1/8 in pass 2, 64 in pass 3): 8 TB (j ^ s) + 8 q + 8 TB T r, s = (j >> 3) & SW;
-//          for T = 80 and SW = 3 odd r use s ^ 2                                   (constant + immediate)
+//   loads  e = j + T r (T = N1/8 in pass 2, 64 in pass 3): 8 TB (j ^ s_r) + 8 q + 8 TB T r with
+//          s_r = ((j >> 3) + (T / 8) r) & SW: one of SW + 1 per-thread bases, picked by r at compile time
+//          (T = 64: s_r = s_0; T = 80: s_0 or s_0 + 2; T = 72: s_0 + r)         (constant + immediate)
 //   stores e = 8 j + r (pass 1)                    : (8 TB (8 j + (j & SW)) + 8 q) ^ (8 TB r)
 //   stores e = 64 (j >> 3) + (j & 7) + 8 r (pass 2): (8 TB (64 (j >> 3) + (j & 7)) + 8 q) ^ (8 TB (8 r + (r & SW)))
 // The (constant ^ immediate) form needs the buffer base aligned to 8 TB 64 bytes; col_buffer_base()
@@ -245,15 +286,14 @@ template <int TB> struct ColLayout {
 
 template <int TB>
 struct ColAddr {
-    unsigned ld_a, ld_b, st1, st2;
+    unsigned ld[ColLayout<TB>::SW + 1], st1, st2;          // ld[k]: swizzle term ((j >> 3) + k) & SW
     __device__ __forceinline__ ColAddr(const void* raw, int j, int q)
     {
         constexpr int SW = ColLayout<TB>::SW;
         constexpr unsigned AL = ColLayout<TB>::ALIGN;
         const unsigned sb = ((smem_addr(raw) + AL - 1u) & ~(AL - 1u)) + 8u * (unsigned)q;
-        const int s = (j >> 3) & SW;
-        ld_a = sb + 8u * TB * (unsigned)(j ^ s);
-        ld_b = sb + 8u * TB * (unsigned)(j ^ ((s + 2) & SW));
+#pragma unroll
+        for (int k = 0; k <= SW; ++k) ld[k] = sb + 8u * TB * (unsigned)(j ^ (((j >> 3) + k) & SW));
         st1 = sb + 8u * TB * (unsigned)(8 * j + (j & SW));
         st2 = sb + 8u * TB * (unsigned)(64 * (j >> 3) + (j & 7));
     }
@@ -265,15 +305,15 @@ struct ColAddr {
 template <int TB, int T, int R, int OFF = 0> struct ColLoad {
     template <int r> static __device__ __forceinline__ c2 one(const ColAddr<TB>& A)
     {
-        // ((j >> 3) + (T / 8) r) & SW differs from (j >> 3) & SW only for T = 80, SW = 3, odd r
-        constexpr bool alt = (T == 80) && (ColLayout<TB>::SW == 3) && (r & 1);
-        return lds<OFF + 8 * TB * T * r>(alt ? A.ld_b : A.ld_a);
+        static_assert(T % 8 == 0, "butterfly count must be a multiple of 8");
+        return lds<OFF + 8 * TB * T * r>(A.ld[((T / 8) * r) & ColLayout<TB>::SW]);
     }
     static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* v)
     {
         v[0] = one<0>(A); v[1] = one<1>(A); v[2] = one<2>(A); v[3] = one<3>(A);
         v[4] = one<4>(A); v[5] = one<5>(A); v[6] = one<6>(A); v[7] = one<7>(A);
-        if (R == 10) { v[8] = one<8>(A); v[9] = one<9>(A); }
+        if (R >= 9) v[8] = one<8>(A);
+        if (R >= 10) v[9] = one<9>(A);
     }
 };
 // 128-bit variants: a thread owns two adjacent columns (q even), whose words are adjacent in the exchange buffer
@@ -288,14 +328,15 @@ __device__ __forceinline__ void sts128(unsigned a, c2 x, c2 y)
 template <int TB, int T, int R, int OFF = 0> struct ColLoad2 {
     template <int r> static __device__ __forceinline__ void one(const ColAddr<TB>& A, c2* va, c2* vb)
     {
-        constexpr bool alt = (T == 80) && (ColLayout<TB>::SW == 3) && (r & 1);
-        lds128<OFF + 8 * TB * T * r>(alt ? A.ld_b : A.ld_a, va[r], vb[r]);
+        static_assert(T % 8 == 0, "butterfly count must be a multiple of 8");
+        lds128<OFF + 8 * TB * T * r>(A.ld[((T / 8) * r) & ColLayout<TB>::SW], va[r], vb[r]);
     }
     static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* va, c2* vb)
     {
         one<0>(A, va, vb); one<1>(A, va, vb); one<2>(A, va, vb); one<3>(A, va, vb);
         one<4>(A, va, vb); one<5>(A, va, vb); one<6>(A, va, vb); one<7>(A, va, vb);
-        if (R == 10) { one<8>(A, va, vb); one<9>(A, va, vb); }
+        if (R >= 9) one<8>(A, va, vb);
+        if (R >= 10) one<9>(A, va, vb);
     }
 };
 template <int TB, unsigned OFF = 0>

@@ -121,13 +121,9 @@ void launch_inverse(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lon
                     cudaStream_t st);
 // returns the number of kernels launched
 
-// corr_inv.cu: the register-resident packed-arithmetic kernels for M = N1 x 512, N1 in {512, 640}
+// corr_inv.cu: the register-resident packed-arithmetic kernels for M = N1 x 512, N1 in {512, 576, 640}
 bool corr_inv_supported(const Fft4Plan& P);
 size_t corr_inv_desc_bytes(int nunits);
-// Phase-1 unit tiling of the fused persistent kernel (0 x 0: fused kernel disabled) and the number of unit
-// positions a dense launch sequence has to cover for ns clips x nb chunks.
-void corr_inv_tiling(int* tile_clips, int* tile_chunks);
-long long corr_inv_dense_units(int ns, int nb);
 void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, long long spec_slab, const UnitSrc& U,
                      int nunits, float2* scratch, void* desc, const InvOut& out, bool write, cudaStream_t st);
 
