@@ -165,3 +165,75 @@ def make_stream_device(seconds: float, patterns: list[dict[str, Any]], sr: int =
             audio[start:start + L] += g * pt
             plants.append((p["name"], start, g))
     return audio, plants
+
+
+def _block_noise(block: int, block_size: int, seed: int, bed_sigma: float, device: str):
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed((seed * 1000003 + block) & 0x7FFFFFFFFFFF)
+    return torch.randn(block_size, generator=gen, dtype=torch.float32, device=device) * bed_sigma
+
+
+def make_stream_slab_device(seconds_total: float, patterns: list[dict[str, Any]], sr: int, seed: int,
+                            plants_per_pattern: int, chunk_seconds: int, lo: int, hi: int, bed_sigma: float = 0.1,
+                            gains: tuple[float, ...] = (1.0, 0.5), device: str = "cuda"):
+    """Samples [lo, hi) of ONE logical stream of ``seconds_total`` seconds, generated on the device so that every
+    process of a sharded scan (any world size) sees the same stream: the noise bed is drawn per fixed 4 Mi-sample
+    block from a generator seeded by (seed, block index), the one-pole low-pass carries across blocks through the
+    previous block's last 31 noise samples, and the plant list is planned for the whole stream on the host and applied
+    where it overlaps the slab.  Returns (float32 CUDA tensor of hi - lo samples, plants of the whole stream)."""
+    import torch
+    n = int(round(seconds_total * sr))
+    lo, hi = max(0, int(lo)), min(n, int(hi))
+    bs = 1 << 22
+    out = torch.empty(max(0, hi - lo), dtype=torch.float32, device=device)
+    taps = torch.tensor([0.5 ** (k + 1) for k in range(32)], dtype=torch.float32, device=device).flip(0).view(1, 1, -1)
+    for b in range(lo // bs, (hi + bs - 1) // bs if hi > lo else 0):
+        w = _block_noise(b, bs, seed, bed_sigma, device)
+        prev = _block_noise(b - 1, bs, seed, bed_sigma, device)[-31:] if b > 0 else torch.zeros(31, device=device)
+        y = torch.nn.functional.conv1d(torch.cat([prev, w]).view(1, 1, -1), taps).view(-1)
+        a, e = max(lo, b * bs), min(hi, (b + 1) * bs)
+        out[a - lo:e - lo] = y[a - b * bs:e - b * bs]
+    rs = np.random.RandomState(seed + 1000003)
+    C = int(chunk_seconds * sr)
+    plants: list[tuple[str, int, float]] = []
+    taken = np.zeros((n + C - 1) // C + 1, dtype=np.int32)
+    spans: list[tuple[int, int]] = []
+    for pi, p in enumerate(patterns):
+        L = p["audio"].size
+        if L + 2 >= n:
+            continue
+        pt = None
+        for k in range(plants_per_pattern):
+            for _attempt in range(50):
+                if k % 6 == 0 and n > C + L:
+                    b0 = int(rs.randint(1, max(2, n // C))) * C
+                    start = b0 - int(rs.randint(1, L))
+                else:
+                    start = int(rs.randint(0, n - L - 1))
+                if start < 0 or start + L >= n:
+                    continue
+                pad = L if p.get("strategy") == "marker_tone" else 0
+                a0, a1 = max(0, start - pad), min(n, start + L + pad)
+                c0, c1 = a0 // C, a1 // C
+                if taken[c0:c1 + 1].max() >= 2:
+                    continue
+                if any(a0 < e and s_ < a1 for s_, e in spans[-4096:] if abs(s_ - a0) < 4 * C):
+                    continue
+                break
+            else:
+                continue
+            taken[c0:c1 + 1] += 1
+            spans.append((a0, a1))
+            g = float(gains[(pi + k) % len(gains)])
+            plants.append((p["name"], start, g))
+            if a1 <= lo or a0 >= hi:
+                continue
+            if pt is None:
+                pt = torch.from_numpy(p["audio"]).to(device)
+            duck = 0.02 if p.get("strategy") == "marker_tone" else 0.1
+            out[max(a0, lo) - lo:min(a1, hi) - lo] *= duck
+            s0, s1 = max(start, lo), min(start + L, hi)
+            if s1 > s0:
+                out[s0 - lo:s1 - lo] += g * pt[s0 - start:s1 - start]
+    return out, plants

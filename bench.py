@@ -1,14 +1,22 @@
 #!/usr/bin/env python
-"""Headline benchmark: audio-hours scanned per second (8 kHz, 64 patterns, 60 s chunks) on N B200s.
+"""Headline benchmark: audio-hours scanned per second on N B200s.
 
-    python bench.py --gpus N --steps K --warmup W            # B200 path
-    python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle port, all host cores)
+    python bench.py --gpus N --steps K --warmup W                  # B200 path, workload c3 (the headline)
+    python bench.py --workload c4|c5 ...                           # the other BASELINE.json configs
+    python bench.py --impl reference --steps K --warmup W          # CPU arm (oracle port, all host cores)
 
-A "step" is one pass of the detection hot path over a whole synthetic stream
-(BASELINE.json configs[2]: 24 h of 8 kHz radio x 64 patterns of 0.3-10 s, 60 s chunks =
-92,160 (chunk x pattern) units) per GPU.  Streams are generated per rank on the device
-(weak scaling: every GPU scans its own 24 h slab, no collective on the data path; torch.distributed
-is used only for the barrier and the max-over-ranks of the step time).
+Workloads (BASELINE.json configs):
+  c3 (default, configs[2]): 24 h of synthetic 8 kHz radio per GPU x 64 patterns of 0.3-10 s, 60 s chunks =
+      92,160 (chunk x pattern) units per GPU and step.  Every rank scans its own stream (weak scaling).
+  c4 (configs[3]): 16 kHz, 256 patterns, --chunk-seconds auto (2 * ceil(longest clip) = 20 s), 24 h per GPU (weak).
+  c5 (configs[4]): ONE logical 8 kHz archive x 256 patterns sharded by contiguous chunk ranges (+ look-back halo) over
+      the ranks; the accepted detections are gathered to rank 0 through the host (gloo) inside the timed region and
+      checked against single-GPU scans of fixed chunk windows (strong scaling).  --hours sets the archive length
+      (default 240 h so that the default run ends within minutes; 1000 h fits one B200: 115 GB of float32).
+
+A "step" is one pass of the detection hot path over the whole workload.  Streams are generated on the device; there is
+no collective on the data path: torch.distributed is used for the barrier, the max-over-ranks of the step time and
+(c5) the host-side gather of the detections.
 
 JSON keys are described in DESIGN.md section "Measurement".
 """
@@ -16,6 +24,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,16 +36,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "audio-hours scanned/sec (8 kHz, 64 patterns, 60 s chunks)"
 UNIT = "audio-hours/s"
-SR = 8000
-SPC = 60
-N_PATTERNS = 64
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel pair from the committed ncu --set full
-# capture (profiles/ncu_r1_end_corr_summary.txt, end of round 1; profiles/ncu_r1_corr_summary.txt earlier: 3.238 GB),
-# scaled from the captured launches to one step: one 512-unit launch pair of the 640 x 512 shape moves 3.265 GB
-# (k_corr_rows 0.443 r + 1.284 w, k_corr_cols2 1.534 r + 0.004 w) = 6.38 MB/unit; the 512 x 512 shape scales with M
-TRAFFIC_BYTES_PER_STEP = int(49 * 1440 * 3.265e9 / 512 + 15 * 1440 * 3.265e9 / 512 * 0.8)
+WORKLOADS = {
+    "c3": {"sr": 8000, "spc": 60, "patterns": 64, "hours": 24.0, "scaling": "weak",
+           "metric": "audio-hours scanned/sec (8 kHz, 64 patterns, 60 s chunks)",
+           "desc": "synthetic 8 kHz radio x 64 patterns (0.3-10 s), 60 s chunks (BASELINE configs[2])"},
+    "c4": {"sr": 16000, "spc": None, "patterns": 256, "hours": 24.0, "scaling": "weak",
+           "metric": "audio-hours scanned/sec (16 kHz, 256 patterns, auto chunk seconds)",
+           "desc": "synthetic 16 kHz radio x 256 patterns (0.3-10 s), auto chunk seconds = 20 s (BASELINE configs[3])"},
+    "c5": {"sr": 8000, "spc": 60, "patterns": 256, "hours": 240.0, "scaling": "strong",
+           "metric": "audio-hours scanned/sec (8 kHz, 256 patterns, 60 s chunks, one archive sharded by chunk ranges)",
+           "desc": "one synthetic 8 kHz archive x 256 patterns (0.3-10 s), 60 s chunks, sharded by contiguous chunk "
+                   "ranges + halo, detections gathered to rank 0 (BASELINE configs[4])"},
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel pair from the committed ncu --set full capture
+# (profiles/ncu_r2_b_summary.txt): one 416-unit launch pair of the 640 x 512 shape moves 2.659 GB (k_corr_rows
+# 0.396 r + 1.033 w, k_corr_cols 1.226 r + 0.004 w) = 6.39 MB/unit; the other shapes scale with M = N1 x 512
+TRAFFIC_BYTES_PER_UNIT_640 = 2.659e9 / 416
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -103,75 +119,107 @@ def bind_to_gpu_numa_node(index: int) -> None:
         pass
 
 
-def cpu_oracle_rate(patterns, audio_np: np.ndarray, n_chunks: int, procs: int) -> tuple[float, float, int]:
-    """Oracle port (oracle/detector.py) over chunks [1, 1+n_chunks) of audio_np, sharded over `procs`
-    processes (each chunk keeps its look-back halo).  Returns (audio-hours/s, seconds, units)."""
+# ----------------------------------------------------------------------------------------------------------- CPU arm
+_CPU_JOB = None
+
+
+def _cpu_worker(rng):
+    """Oracle port over chunks [rng[0], rng[1]): returns (units, [(chunk, clip index, peak, accept)], seconds)."""
+    from oracle.detector import OracleDetector
+    patterns, audio, sr, spc = _CPU_JOB
+    det = OracleDetector(patterns, sr, spc, precision="f32")
+    names = {p["name"]: i for i, p in enumerate(patterns)}
+    n = [0]
+    cands: list[tuple[int, int, int, int]] = []
+
+    def on_unit(i, st, tr):
+        n[0] += 1
+        for c in tr["candidates"]:
+            if c["kind"] != "skipped":
+                cands.append((int(i), names[st.name], int(c["peak"]), int(bool(c["accept"]))))
+
+    t0 = time.perf_counter()
+    det.run(audio, on_unit=on_unit, chunk_range=rng)
+    return n[0], cands, time.perf_counter() - t0
+
+
+def cpu_oracle_rate(patterns, audio_np: np.ndarray, sr: int, spc: int, n_chunks: int, procs: int):
+    """Oracle port (oracle/detector.py) over chunks [1, 1 + n_chunks) of audio_np, sharded over `procs` processes
+    (each chunk keeps its look-back halo).  Returns (audio-hours/s, seconds, units, candidate list)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     first = 1
     bounds = np.linspace(first, first + n_chunks, procs + 1).astype(int)
     jobs = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
     global _CPU_JOB
-    _CPU_JOB = (patterns, audio_np)
+    _CPU_JOB = (patterns, audio_np, sr, spc)
     t0 = time.perf_counter()
-    with ctx.Pool(len(jobs)) as pool:
-        res = pool.map(_cpu_worker, jobs)
+    if len(jobs) == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with ctx.Pool(len(jobs)) as pool:
+            res = pool.map(_cpu_worker, jobs)
     dt = time.perf_counter() - t0
-    hours = n_chunks * SPC / 3600.0
-    return hours / dt, dt, sum(res)
+    hours = n_chunks * spc / 3600.0
+    cands = [c for r in res for c in r[1]]
+    return hours / dt, dt, sum(r[0] for r in res), cands
 
 
-_CPU_JOB = None
+def workload_config(args, wl, hours, n_chunks_per_gpu=None) -> dict:
+    cfg = {"workload": f"{args.workload}: {wl['desc']}", "hours_per_step": hours, "patterns": wl["patterns"],
+           "sample_rate": wl["sr"]}
+    return cfg
 
 
-def _cpu_worker(rng):
-    from oracle.detector import OracleDetector
-    patterns, audio = _CPU_JOB
-    det = OracleDetector(patterns, SR, SPC, precision="f32")
-    n = [0]
-    det.run(audio, on_unit=lambda i, st, tr: n.__setitem__(0, n[0] + 1), chunk_range=rng)
-    return n[0]
+def auto_spc(patterns, sr):
+    return int(math.ceil(max(p["audio"].size for p in patterns) / sr)) * 2       # apd.py:117-120
 
 
 def run_reference(args) -> None:
-    """CPU arm: the oracle port of the reference path (the reference's Rust/wheel natives cannot be
-    installed offline), all host cores, bounded sample of the same workload."""
+    """CPU arm: the oracle port of the reference path (the reference's Rust / wheel natives cannot be installed
+    offline), all host cores, bounded sample of the same workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from audio_pattern_detector_b200 import workloads as W
     from oracle import native
     native.build()
+    wl = WORKLOADS[args.workload]
+    sr = wl["sr"]
     cores = os.cpu_count() or 1
-    patterns = W.make_patterns(N_PATTERNS, SR, seed=1)
+    patterns = W.make_patterns(wl["patterns"], sr, seed=1)
+    spc = wl["spc"] or auto_spc(patterns, sr)
     per_step = max(cores, 4) * args.cpu_chunks_per_core
-    audio, _ = W.make_stream((per_step + 2) * SPC, patterns, SR, seed=0, plants_per_pattern=1, chunk_seconds=SPC)
+    audio, _ = W.make_stream((per_step + 2) * spc, patterns, sr, seed=0, plants_per_pattern=1, chunk_seconds=spc)
     rates, secs = [], []
     for s in range(args.warmup + args.steps):
-        r, dt, units = cpu_oracle_rate(patterns, audio, per_step, cores)
+        r, dt, units, _ = cpu_oracle_rate(patterns, audio, sr, spc, per_step, cores)
         if s >= args.warmup:
             rates.append(r)
             secs.append(dt)
     value = float(np.mean(rates))
-    sample = f"{per_step} chunks x {N_PATTERNS} patterns ({per_step * N_PATTERNS} units) of the same workload per step"
+    hours = args.hours if args.hours else wl["hours"]
+    sample = (f"{per_step} chunks x {wl['patterns']} patterns ({per_step * wl['patterns']} units) of the same workload "
+              f"per step, scaled linearly")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1000,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "8 kHz synthetic radio x 64 patterns (0.3-10 s), 60 s chunks (configs[2])",
-                   "chunk_seconds": SPC, "patterns": N_PATTERNS},
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl, hours),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ----------------------------------------------------------------------------------------------------------- B200 arm
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--hours", type=float, default=24.0, help="audio hours per GPU per step")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--hours", type=float, default=0.0, help="audio hours per GPU (c3, c4) or of the archive (c5) per step")
     ap.add_argument("--batch-chunks", type=int, default=48)
     ap.add_argument("--cpu-chunks-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -192,39 +240,70 @@ def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    host_group = None
     if world > 1:
         bind_to_gpu_numa_node(local)      # before any pinned allocation: host buffers on the GPU's own socket
         dist.init_process_group("nccl", device_id=torch.device(dev))
+        host_group = dist.new_group(backend="gloo")       # host-side gather of the detections (c5)
 
+    from audio_pattern_detector_b200 import sharding
     from audio_pattern_detector_b200 import workloads as W
     from audio_pattern_detector_b200.audio_clip import AudioClip
     from audio_pattern_detector_b200.audio_pattern_detector import AudioPatternDetector
 
-    patterns = W.make_patterns(N_PATTERNS, SR, seed=1)
-    seconds = args.hours * 3600.0
-    audio, plants = W.make_stream_device(seconds, patterns, SR, seed=rank, plants_per_pattern=max(1, int(args.hours)),
-                                         chunk_seconds=SPC, device=dev)
-    n = audio.numel()
-    n_chunks = (n + SPC * SR - 1) // (SPC * SR)
-    host = torch.empty(n, dtype=torch.float32).pin_memory()
-    host.copy_(audio)
-    torch.cuda.synchronize()
-
-    clips = [AudioClip(name=p["name"], audio=p["audio"], sample_rate=SR, strategy=p["strategy"],
+    wl = WORKLOADS[args.workload]
+    sr, n_pat = wl["sr"], wl["patterns"]
+    hours = args.hours if args.hours else wl["hours"]
+    strong = wl["scaling"] == "strong"
+    patterns = W.make_patterns(n_pat, sr, seed=1)
+    spc = wl["spc"] or auto_spc(patterns, sr)
+    C_ = spc * sr
+    seconds = hours * 3600.0
+    clips = [AudioClip(name=p["name"], audio=p["audio"], sample_rate=sr, strategy=p["strategy"],
                        strategy_params=p["strategy_params"]) for p in patterns]
     import logging
     logging.getLogger("audio_pattern_detector_b200").setLevel(logging.ERROR)
     sys.stderr, saved = open(os.devnull, "w"), sys.stderr
-    det = AudioPatternDetector(audio_clips=clips, seconds_per_chunk=SPC, target_sample_rate=SR,
+    det = AudioPatternDetector(audio_clips=clips, seconds_per_chunk=wl["spc"], target_sample_rate=sr,
                                device=local, max_batch_chunks=args.batch_chunks)
     sys.stderr = saved
+    assert det.seconds_per_chunk == spc
+    plants_per = max(1, int(hours))
+
+    if strong:
+        # one logical archive: this rank holds chunks [c0, c1) plus the look-back halo, generated from the global seed
+        n_total = int(round(seconds * sr))
+        n_chunks_total = (n_total + C_ - 1) // C_
+        c0, c1 = sharding.chunk_range_for_rank(n_chunks_total, world, rank)
+        lo, hi = sharding.slab_bounds(c0, c1, C_, det._max_halo, n_total)
+        audio, plants = W.make_stream_slab_device(seconds, patterns, sr, 0, plants_per, spc, lo, hi, device=dev)
+        scan_kw = dict(chunk_range=(c0, c1), base_sample=lo, total_samples=n_total)
+        my_chunks = list(range(c0, c1))
+    else:
+        audio, plants = W.make_stream_device(seconds, patterns, sr, seed=rank, plants_per_pattern=plants_per,
+                                             chunk_seconds=spc, device=dev)
+        n_total = audio.numel()
+        n_chunks_total = (n_total + C_ - 1) // C_
+        lo, c0, c1 = 0, 0, n_chunks_total
+        scan_kw = {}
+        my_chunks = list(range(n_chunks_total))
+    n = audio.numel()
+    torch.cuda.synchronize()
+
+    # algorithmic bytes of this rank's units: 8 * N_out, N_out = section + L - 1
+    L_arr = np.asarray([p["audio"].size for p in patterns], dtype=np.int64)
+    sw_arr = np.asarray([math.ceil(p["audio"].size / sr) for p in patterns], dtype=np.int64) * sr
     alg_bytes = 0
-    for ci in (0, 1):
-        for p in range(N_PATTERNS):
-            nb = 8 * det.unit_n_out(ci, p, n)
-            alg_bytes += nb * (1 if ci == 0 else n_chunks - 2)
-    for p in range(N_PATTERNS):
-        alg_bytes += 8 * det.unit_n_out(n_chunks - 1, p, n)
+    n_units = 0
+    mids = [ci for ci in my_chunks if 0 < ci < n_chunks_total - 1]
+    alg_bytes += len(mids) * int(np.sum(8 * (C_ + sw_arr + L_arr - 1)))
+    for ci in my_chunks:
+        if 0 < ci < n_chunks_total - 1:
+            continue
+        last_len = min(C_, n_total - ci * C_)
+        sec = last_len + (sw_arr if ci > 0 else 0)
+        alg_bytes += int(np.sum(8 * (sec + L_arr - 1)))
+    n_units = len(my_chunks) * n_pat
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,9 +327,29 @@ def main() -> None:
             ms = float(t.item())
         return ms / steps, out
 
-    # inputs (2.8 GB/GPU) exceed the 126 MB L2, so every step re-reads them from HBM
-    resident = lambda: det.scan_array(audio)            # noqa: E731
-    through_host = lambda: det.scan_array(host)         # noqa: E731  (pinned host buffer -> H2D inside the call)
+    def accepted_table(res):
+        r = res.records
+        keep = (r["flags"] & 1) != 0
+        return np.stack([r["chunk"][keep], r["clip"][keep], r["peak"][keep]], axis=1).astype(np.int64)
+
+    gathered_box: list = [None]
+
+    def gather(res):
+        """c5: every rank's accepted (chunk, clip, peak) rows travel to rank 0 through the host (gloo)."""
+        if not strong or world == 1:
+            gathered_box[0] = [accepted_table(res)]
+            return res
+        out = [None] * world if rank == 0 else None
+        dist.gather_object(accepted_table(res), out, dst=0, group=host_group)
+        gathered_box[0] = out
+        return res
+
+    # inputs (GBs per GPU) exceed the 126 MB L2, so every step re-reads them from HBM
+    resident = lambda: gather(det.scan_array(audio, **scan_kw))                      # noqa: E731
+    host = torch.empty(n, dtype=torch.float32).pin_memory()
+    host.copy_(audio)
+    torch.cuda.synchronize()
+    through_host = lambda: gather(det.scan_array(host, **scan_kw))                   # noqa: E731  (pinned host -> H2D inside)
 
     for _ in range(args.warmup):
         res = resident()
@@ -266,72 +365,121 @@ def main() -> None:
     stages = {k: v / args.steps for k, v in det.stage_times_ms(reset=True).items()}
     det.enable_profiling(False)
     through_host()                                       # untimed: first-use allocations of the host-input path
-    ms_e2e, res_h = timed(through_host, max(1, min(args.steps, 2)))
+    ms_e2e, res_h = timed(through_host, args.steps)
     assert res_h.peak_times == res.peak_times
 
-    # row N1 (streaming ingestion): the same scan from 16-bit PCM in pinned host memory -- half the PCIe bytes, widened
-    # to float32 on the device (apd_pcm_to_float); the stream is the synthetic one quantised to int16
-    pcm = (audio * 32768.0).round_().clamp_(-32768, 32767).to(torch.int16).cpu().pin_memory()
-    through_pcm = lambda: det.scan_array(pcm)           # noqa: E731
-    through_pcm()
-    ms_pcm, res_p = timed(through_pcm, max(1, min(args.steps, 2)))
-    del pcm
+    extra: dict = {}
+    if args.workload == "c3":
+        # row N1 (streaming ingestion): the same scan from 16-bit PCM in pinned host memory -- half the PCIe bytes,
+        # widened to float32 on the device (apd_pcm_to_float); the stream is the synthetic one quantised to int16
+        pcm = (audio * 32768.0).round_().clamp_(-32768, 32767).to(torch.int16).cpu().pin_memory()
+        through_pcm = lambda: det.scan_array(pcm)           # noqa: E731
+        through_pcm()
+        ms_pcm, res_p = timed(through_pcm, args.steps)
+        del pcm
+        extra["e2e_pcm16"] = {"value": hours * world / (ms_pcm / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(n * 2),
+                              "ms_per_step": ms_pcm,
+                              "detections_per_step": sum(len(v) for v in res_p.peak_times.values()),
+                              "note": "same scan from int16 PCM in pinned host memory, widened on the device (row N1)"}
 
-    # the dominant stage timed alone (nothing else on the GPU), for the roofline of the kernel itself; the
-    # in-step figure above shares the SMs with the overlapped phase-2 and loudness streams
-    iso_ms, iso_launches = det.time_correlate_stage(audio)
+    # the dominant stage timed alone (nothing else on the GPU), for the roofline of the kernel itself; the in-step
+    # figure shares the SMs with the overlapped phase-2 and loudness streams
+    iso_ms, iso_launches = (det.time_correlate_stage(audio) if not strong else (float("nan"), 0))
 
-    hours_total = args.hours * world
+    hours_total = hours if strong else hours * world
     value = hours_total / (ms_step / 1000.0)
     e2e_value = hours_total / (ms_e2e / 1000.0)
     n_det = sum(len(v) for v in res.peak_times.values())
     peak, peak_src = measured_peak_gbs()
-    achieved_in_step = alg_bytes / 1e9 / (stages["correlate_max"] / 1000.0)
-    achieved = alg_bytes / 1e9 / (iso_ms / 1000.0)
+
+    # c5: the gathered detections against single-GPU scans of fixed chunk windows of the same archive
+    shard_check = None
+    if strong and rank == 0:
+        tab = np.concatenate([t for t in gathered_box[0] if t is not None and len(t)] or [np.zeros((0, 3), np.int64)])
+        windows = sorted({0, n_chunks_total // 4, n_chunks_total // 2, (3 * n_chunks_total) // 4,
+                          max(0, n_chunks_total - 3)})
+        checked = mismatched = 0
+        for w0 in windows:
+            w1 = min(n_chunks_total, w0 + 3)
+            wlo, whi = sharding.slab_bounds(w0, w1, C_, det._max_halo, n_total)
+            slab, _ = W.make_stream_slab_device(seconds, patterns, sr, 0, plants_per, spc, wlo, whi, device=dev)
+            ref = accepted_table(det.scan_array(slab, chunk_range=(w0, w1), base_sample=wlo, total_samples=n_total))
+            got = tab[(tab[:, 0] >= w0) & (tab[:, 0] < w1)]
+            checked += (w1 - w0) * n_pat
+            a = {tuple(r) for r in ref.tolist()}
+            b = {tuple(r) for r in got.tolist()}
+            mismatched += len(a ^ b)
+        shard_check = {"chunk_windows": [[w, min(n_chunks_total, w + 3)] for w in windows], "units": checked,
+                       "mismatches": mismatched, "gathered_detections": int(tab.shape[0])}
 
     if rank == 0:
+        cfg = workload_config(args, wl, hours)
+        cfg.update({"units_per_step": int(n_chunks_total * n_pat * (1 if strong else world)),
+                    "chunk_seconds": spc, "batch_chunks": args.batch_chunks,
+                    "l2": f"inputs ({n * 4 / 1e9:.1f} GB/GPU) larger than L2; no flush needed",
+                    "detections_per_step": n_det if not strong else int(shard_check["gathered_detections"]),
+                    "planted": len(plants)})
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.hours:g} h synthetic 8 kHz radio per GPU x 64 patterns (0.3-10 s), "
-                                   "60 s chunks (BASELINE configs[2])",
-                       "units_per_step_per_gpu": int(n_chunks * N_PATTERNS), "batch_chunks": args.batch_chunks,
-                       "l2": "inputs (2.8 GB/GPU) larger than L2; no flush needed",
-                       "detections_per_step": n_det, "planted": len(plants)},
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 4),
-                    "d2h_bytes_per_step": int(res.n_candidates * 176 + n_chunks // args.batch_chunks * 64),
-                    "ms_per_step": ms_e2e},
-            "e2e_pcm16": {"value": hours_total / (ms_pcm / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(n * 2),
-                          "ms_per_step": ms_pcm, "detections_per_step": sum(len(v) for v in res_p.peak_times.values()),
-                          "note": "same scan from int16 PCM in pinned host memory, widened on the device (row N1)"},
+                    "d2h_bytes_per_step": int(res.n_candidates * 176 + max(1, len(my_chunks) // args.batch_chunks) * 64),
+                    "ms_per_step": ms_e2e, "steps": args.steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "stage_ms": stages,
-            "roofline": {"bound": "hbm", "kernel": "fused spectral multiply + inverse FFT + |.| + max "
-                                                   "(k_corr_rows + k_corr_cols2)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_STEP, "algorithmic_bytes_per_step": int(alg_bytes),
-                         "peak_source": peak_src,
-                         "timing": "stage timed alone over the whole workload (CUDA events, apd_stage_correlate_max "
-                                   "per sub-batch after untimed loudness + forward stages)",
-                         "stage_ms_alone": iso_ms, "launches_alone": int(iso_launches),
-                         "in_step": {"achieved": achieved_in_step, "frac": achieved_in_step / peak,
-                                     "stage_ms": stages["correlate_max"],
-                                     "note": "same stage inside the timed step, sharing the SMs with the "
-                                             "overlapped phase-2 and loudness streams"}},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        line.update(extra)
+        if shard_check is not None:
+            line["sharded_check"] = shard_check
+        if not strong:
+            achieved = alg_bytes / 1e9 / (iso_ms / 1000.0)
+            achieved_in_step = alg_bytes / 1e9 / (stages["correlate_max"] / 1000.0)
+            # DRAM traffic of the pair per step, from the ncu capture of the 640 x 512 shape scaled by M per shape class
+            m_of = lambda no: 512 * (512 if no <= 524288 else (576 if no <= 589824 else 640))        # noqa: E731
+            traffic = sum(TRAFFIC_BYTES_PER_UNIT_640 * m_of(int(C_ + s + L - 1)) / (640 * 512)
+                          for s, L in zip(sw_arr, L_arr)) * len(my_chunks)
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "fused spectral multiply + inverse FFT + |.| + max (k_corr_rows + k_corr_cols)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": int(traffic), "algorithmic_bytes_per_step": int(alg_bytes), "peak_source": peak_src,
+                "timing": "stage timed alone over the whole workload (CUDA events, apd_stage_correlate_max per "
+                          "sub-batch after untimed loudness + forward stages)",
+                "stage_ms_alone": iso_ms, "launches_alone": int(iso_launches),
+                "in_step": {"achieved": achieved_in_step, "frac": achieved_in_step / peak,
+                            "stage_ms": stages["correlate_max"],
+                            "note": "same stage inside the timed step, sharing the SMs with the overlapped phase-2 "
+                                    "and loudness streams"}}
+        if world == 1 and not args.no_cpu_baseline and not strong:
+            # CPU baseline on the box's host cores, on chunks 1..nck of the SAME stream; its detections are the
+            # parity check of the timed GPU result on those chunks (peaks and accept flags must be identical)
             cores = os.cpu_count() or 1
             nck = max(cores, 4) * args.cpu_chunks_per_core
-            sample_audio = host[: (nck + 2) * SPC * SR].numpy().copy()
-            rate, dt, units = cpu_oracle_rate(patterns, sample_audio, nck, cores)
+            sample_audio = host[: (nck + 2) * C_].numpy().copy()
+            rate, dt, units, ocands = cpu_oracle_rate(patterns, sample_audio, sr, spc, nck, cores)
+            n1 = max(1, min(2, nck))
+            rate1, dt1, units1, _ = cpu_oracle_rate(patterns, sample_audio, sr, spc, n1, 1)
+            r = res.records
+            sel = (r["chunk"] >= 1) & (r["chunk"] < 1 + nck) & ((r["flags"] & 2) == 0)
+            gcands = {(int(a), int(b), int(c), int(f) & 1) for a, b, c, f in
+                      zip(r["chunk"][sel], r["clip"][sel], r["peak"][sel], r["flags"][sel])}
+            mism = len(gcands ^ set(ocands))
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"chunks 1..{nck} of the same stream x 64 patterns ({units} units), "
-                                              f"{dt:.1f} s wall; oracle port of the reference's scipy-style CPU path"}
+                                    "sample": f"chunks 1..{nck} of the same stream x {n_pat} patterns ({units} units), "
+                                              f"{dt:.1f} s wall; oracle port of the reference's scipy-style CPU path",
+                                    "single_core": {"value": rate1, "unit": UNIT, "cores": 1,
+                                                    "sample": f"chunks 1..{n1} ({units1} units), {dt1:.1f} s wall; the "
+                                                              "reference as shipped is single-threaded"}}
+            line["parity_checked_units"] = int(units)
+            line["parity_checked_candidates"] = len(ocands)
+            line["parity_mismatches"] = int(mism)
+            if mism:
+                sys.stderr.write(f"PARITY MISMATCH on the bench stream: {sorted(gcands ^ set(ocands))[:10]}\n")
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
