@@ -89,7 +89,7 @@ def lib() -> Any:
 
 
 class ApdError(RuntimeError):
-    pass
+    code = 0            # status code of include/apd_b200.h (4: a workspace list overflowed)
 
 
 def check(rc: int, what: str) -> None:
@@ -97,4 +97,6 @@ def check(rc: int, what: str) -> None:
         msg = lib().apd_last_error().decode("utf-8", "replace")
         if rc == 1:
             raise ValueError(f"{what}: {msg}")
-        raise ApdError(f"{what}: {ERR_NAMES.get(rc, rc)}: {msg}")
+        err = ApdError(f"{what}: {ERR_NAMES.get(rc, rc)}: {msg}")
+        err.code = rc
+        raise err

@@ -234,19 +234,35 @@ class AudioPatternDetector:
         ctx = C.c_void_p()
         L = _lib.lib()
         _lib.check(L.apd_create(C.byref(ctx), self._device, sr, self._chunk_samples,
-                                float(height_min) if height_min is not None else 0.0,
+                                float(height_min) if height_min is not None else float("nan"),
                                 len(audio_clips), descs, self._max_batch), "apd_create")
         self._ctx = ctx
         self._max_halo = max(self._sliding_windows, default=0) * sr
         self._dev_buf = None
         self._pinned = None
         self._cand_buf = None
+        self._cand_cap_boost = 1
 
     # ------------------------------------------------------------------ helpers
     def _fallback_tone_frequency(self, raw: NDArray[np.float32]) -> Optional[float]:
-        """Reference :217-219 derives the frequency from the *normalised* clip; a pure gain
-        (plus clipping at +-1) does not move the dominant bin, so the raw clip is used."""
-        return get_pure_tone_frequency(raw, self.target_sample_rate)
+        """Reference :217-219: a marker-tone clip without a declared frequency gets the dominant frequency of its
+        loudness-NORMALISED samples (gain to -16 LUFS, clamped to +-1 -- the clamp can add harmonics).  The
+        normalisation is the device's (apd_create on the clip alone, read back with apd_clip_normalized)."""
+        sr = self.target_sample_rate
+        L = _lib.lib()
+        desc = (_lib.ClipDesc * 1)()
+        desc[0].samples = raw.ctypes.data_as(C.POINTER(C.c_float))
+        desc[0].length = raw.size
+        desc[0].strategy = _lib.STRATEGY_NORMAL
+        ctx = C.c_void_p()
+        chunk = max(self._chunk_samples, 2 * math.ceil(raw.size / sr) * sr)
+        _lib.check(L.apd_create(C.byref(ctx), self._device, sr, chunk, float("nan"), 1, desc, 1), "apd_create")
+        try:
+            norm = np.empty(raw.size, dtype=np.float32)
+            _lib.check(L.apd_clip_normalized(ctx, 0, norm.ctypes.data_as(C.POINTER(C.c_float))), "apd_clip_normalized")
+        finally:
+            L.apd_destroy(ctx)
+        return get_pure_tone_frequency(norm, sr)
 
     def __del__(self) -> None:
         ctx = getattr(self, "_ctx", None)
@@ -370,12 +386,35 @@ class AudioPatternDetector:
     # ------------------------------------------------------------------ device scan of a chunk range
     def _scan_batch(self, dev_ptr: int, base_sample: int, n_samples: int, chunk_begin: int, chunk_end: int,
                     want_trace: bool) -> tuple["NDArray[Any]", Optional[dict]]:
-        """One apd_scan over chunks [chunk_begin, chunk_end); returns (candidate table, unit trace)."""
+        """apd_scan over chunks [chunk_begin, chunk_end); returns (candidate table, unit trace).  The device lists are
+        sized for the average case of a sub-batch and for the worst case of one chunk (a unit keeps up to N_out / L
+        peaks, e.g. a 0.15 s tone clip inside minutes of steady tone): when a scan reports a workspace overflow the
+        range is scanned again in halves, so dense material costs time, never detections."""
+        try:
+            return self._scan_once(dev_ptr, base_sample, n_samples, chunk_begin, chunk_end, want_trace)
+        except _lib.ApdError as e:
+            if e.code != 4:
+                raise
+            if chunk_end - chunk_begin <= 1:
+                if self._cand_cap_boost >= 1 << 10:
+                    raise
+                self._cand_cap_boost *= 4                      # host-side record buffer: grow and retry
+                self._cand_buf = None
+                return self._scan_batch(dev_ptr, base_sample, n_samples, chunk_begin, chunk_end, want_trace)
+        mid = (chunk_begin + chunk_end) // 2
+        ra, ta = self._scan_batch(dev_ptr, base_sample, n_samples, chunk_begin, mid, want_trace)
+        rb, tb = self._scan_batch(dev_ptr, base_sample, n_samples, mid, chunk_end, want_trace)
+        if ta is not None and tb is not None:
+            ta.update(tb)
+        return np.concatenate([ra, rb]), ta
+
+    def _scan_once(self, dev_ptr: int, base_sample: int, n_samples: int, chunk_begin: int, chunk_end: int,
+                   want_trace: bool) -> tuple["NDArray[Any]", Optional[dict]]:
         torch = _torch()
         L = _lib.lib()
         nb = chunk_end - chunk_begin
         ncl = len(self.audio_clips)
-        cap = max(4096, nb * ncl * 4)
+        cap = max(4096, nb * ncl * 4) * self._cand_cap_boost
         if self._cand_buf is None or len(self._cand_buf) < cap:
             self._cand_buf = (_lib.Candidate * cap)()
         cands = self._cand_buf
@@ -592,6 +631,14 @@ class AudioPatternDetector:
         if rc != _lib.APD_OK:
             raise ValueError(f"unsupported PCM format: {sampwidth * 8}-bit, {channels} channel(s)")
 
+    def _pcm_chunks_fit(self, src: Any) -> bool:
+        sr, C_ = self.target_sample_rate, self._chunk_samples
+        in_sr = int(getattr(src, "pcm_sample_rate", None) or sr)
+        if in_sr == sr:
+            return True
+        Cin = int(C_ * in_sr / sr)                                            # frames per chunk read, match.py:398
+        return Cin >= 1 and int(Cin * sr / in_sr) == C_
+
     def _find_clip_in_pcm(self, src: Any, peak_times: Optional[dict[str, list[float]]],
                           on_pattern_detected: Optional[PatternDetectedCallback]
                           ) -> tuple[dict[str, list[float]] | None, float]:
@@ -632,8 +679,16 @@ class AudioPatternDetector:
                 releases the GIL)."""
                 if hasattr(src, "readinto_pcm"):                              # straight into pinned memory
                     return src.readinto_pcm(pins[which].numpy(), chunks * Cin)
-                data = src.read_pcm(chunks * Cin)
-                got = len(data) // (sampwidth * channels)
+                # a pipe may hand out fewer frames than asked for before its end: read on until the batch is full or
+                # the source is exhausted (a short batch means end of stream below)
+                frame = sampwidth * channels
+                data = b""
+                while len(data) < chunks * Cin * frame:
+                    more = src.read_pcm(chunks * Cin - len(data) // frame)
+                    if not more:
+                        break
+                    data += more
+                got = len(data) // frame
                 if got:
                     pins[which].numpy()[:got * channels] = np.frombuffer(data, dtype=np_dt, count=got * channels)
                 return got
@@ -699,9 +754,11 @@ class AudioPatternDetector:
         events: list[tuple[float, str]] = []
         total_time = 0.0
         src = audio_stream.audio_stream
-        if getattr(src, "pcm_format", None) is not None:
-            # raw integer PCM at the detector's rate (e.g. match._WavFileStreamWrapper on a 16/32-bit WAV): the
-            # frames cross PCIe as they are and are widened on the device (row N1, apd_pcm_to_float)
+        if getattr(src, "pcm_format", None) is not None and self._pcm_chunks_fit(src):
+            # raw integer PCM (e.g. match._WavFileStreamWrapper on a 16/32-bit WAV): the frames cross PCIe as they are
+            # and are widened -- and, at another rate, resampled chunk by chunk -- on the device (rows N1, N2).  A source
+            # rate that does not cut into whole device chunks (e.g. 44 101 Hz) takes the float read() path below, where
+            # the wrapper converts and resamples on the host as the reference does (match.py:393-427)
             return self._find_clip_in_pcm(src, peak_times, on_pattern_detected)
         halo = np.zeros(0, dtype=np.float32)          # tail of the previous batch (look-back)
         chunk_index = 0
@@ -715,22 +772,25 @@ class AudioPatternDetector:
                 parts: list[NDArray[np.float32]] = []
                 while len(parts) < self._stream_read_chunks:
                     data = src.read(self._chunk_size)
+                    # a raw / unbuffered source may return fewer bytes than asked for before its end: keep reading until
+                    # the chunk is full or read() returns b'' (the reference, :296-299, would scan each short read as a
+                    # chunk of its own with misplaced timestamps; buffered sources never get here)
+                    while data and len(data) < self._chunk_size:
+                        more = src.read(self._chunk_size - len(data))
+                        if not more:
+                            break
+                        data += more
                     if not data:
                         eof = True
                         break
-                    chunk = np.frombuffer(data, dtype="float32")
+                    chunk = np.frombuffer(data[:len(data) - len(data) % 4], dtype="float32")
                     total_time += len(chunk) / sr                           # reference :301
                     parts.append(chunk)
                     if len(chunk) != C_:
-                        # a short read is the stream's final chunk (reference :296-299 treats any
-                        # following read as a new chunk; fixed-size device chunks cannot)
-                        eof = True
+                        eof = True                                          # the stream's final, shorter chunk
                         break
                 if not parts:
                     break
-                for k, ch in enumerate(parts[:-1]):
-                    if len(ch) != C_:
-                        raise ValueError("audio stream returned a short chunk before the end of the stream")
                 new = np.concatenate(parts) if len(parts) > 1 else parts[0]
                 n_halo = halo.size
                 n_tot = n_halo + new.size

@@ -399,32 +399,28 @@ static int self_correlation(apd_ctx* c, ClipHost& cl, InitTmp& t)
     return APD_OK;
 }
 
-extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t chunk_samples, float height_min,
+static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_samples, float height_min,
                           int n_clips, const apd_clip_desc* descs, int max_batch_chunks)
 {
-    if (!out || !descs || n_clips <= 0 || chunk_samples <= 0 || max_batch_chunks <= 0)
-        return fail(APD_ERR_INVALID, "apd_create: bad arguments");
     CK(cudaSetDevice(device));
-    apd_ctx* c = new apd_ctx();
     c->device = device;
     c->sr = sample_rate;
     c->C = chunk_samples;
     c->n_clips = n_clips;
     c->maxB = max_batch_chunks;
-    c->height = height_min > 0.0f ? height_min : kDefaultHeight;
+    c->height = std::isnan(height_min) ? kDefaultHeight : height_min;      // NaN: not given (apd.py:520)
     std::string err;
-    if (!kw_config_create(sample_rate, &c->kw, &err)) { delete c; return fail(APD_ERR_UNSUPPORTED, err); }
+    if (!kw_config_create(sample_rate, &c->kw, &err)) return fail(APD_ERR_UNSUPPORTED, err);
 
     // ---- clips and sliding-window groups (reference apd.py:155-161)
     c->clips.resize(n_clips);
     std::map<int, int> sw_to_group;
     for (int p = 0; p < n_clips; ++p) {
         ClipHost& cl = c->clips[p];
-        if (!descs[p].samples || descs[p].length <= 0) { delete c; return fail(APD_ERR_INVALID, "empty clip"); }
+        if (!descs[p].samples || descs[p].length <= 0) return fail(APD_ERR_INVALID, "empty clip");
         cl.L = descs[p].length;
         cl.sw = (int)((cl.L + (long long)sample_rate - 1) / sample_rate);
         if ((long long)2 * cl.sw * sample_rate > chunk_samples) {
-            delete c;
             return fail(APD_ERR_INVALID, "seconds_per_chunk is too small for clip " + std::to_string(p));
         }
         cl.strategy = descs[p].strategy;
@@ -452,7 +448,6 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         c->max_halo = std::max(c->max_halo, g.halo);
         Fft4Plan plan;
         if (plan_min_M_for(n_out) > (1LL << 21) || !build_plan((int)plan_min_M_for(n_out), &plan, &err)) {
-            delete c;
             return fail(APD_ERR_UNSUPPORTED, err.empty() ? "chunk too long for the FFT plan" : err);
         }
         int shape = -1;
@@ -714,7 +709,9 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     use_set(c, 0);
     c->corr_stride = (max_nout + 31) / 32 * 32;
     c->cand_stride = max_nout / 2 + 2;
-    c->peak_stride = (int)std::min<long long>(max_nout / std::max(min_L, 1) + 2, 8192);
+    if (max_nout / std::max(min_L, 1) + 2 > 8192)
+        return fail(APD_ERR_UNSUPPORTED, "shortest clip too short for this chunk length (more than 8190 peaks per unit)");
+    c->peak_stride = (int)(max_nout / std::max(min_L, 1) + 2);
     CK(dalloc(&c->d_corr, (size_t)c->n_slots * c->corr_stride));
     CK(dalloc(&c->d_cand_idx, (size_t)c->n_slots * c->cand_stride));
     CK(dalloc(&c->d_cand_val, (size_t)c->n_slots * c->cand_stride));
@@ -724,7 +721,16 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
     CK(dalloc(&c->d_n_peaks, (size_t)c->n_slots));
     CK(dalloc(&c->d_n_cands, (size_t)c->n_slots));
     CK(dalloc(&c->d_slot_cands, (size_t)c->n_slots * c->peak_stride));
-    c->out_capacity = std::max(4096, B * n_clips * 4);
+    // records: an average of 4 per unit of a sub-batch, and never less than the worst case of ONE chunk (a unit keeps at
+    // most N_out / L + 1 peaks, lib.rs:437-485), so that the caller can always make progress by scanning fewer chunks
+    long long chunk_bound = 0, tone_bound = 0;
+    for (auto& cl : c->clips) {
+        const long long per_unit = max_nout / std::max(cl.L, 1) + 2;
+        chunk_bound += per_unit;
+        if (cl.tone_P > 0) tone_bound += per_unit;
+    }
+    if (chunk_bound > (1LL << 24)) return fail(APD_ERR_UNSUPPORTED, "clips too short for this chunk length (candidate bound)");
+    c->out_capacity = (int)std::max<long long>(std::max(4096, B * n_clips * 4), chunk_bound);
     for (auto& b : used_sets(c)) {
         CK(dalloc(&b.d_out, (size_t)c->out_capacity));
         CK(cudaMallocHost((void**)&b.h_out, sizeof(apd_candidate) * (size_t)c->out_capacity));
@@ -741,7 +747,7 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         c->tone_max_P = max_P;
         for (auto& cl : c->clips)
             if (cl.tone_P > 0) c->tone_max_L = std::max(c->tone_max_L, cl.L);
-        c->tone_item_cap = std::max(4096, B * n_clips);
+        c->tone_item_cap = (int)std::max<long long>(std::max(4096, B * n_clips), tone_bound);
         for (auto& b : used_sets(c)) CK(cudaMalloc(&b.d_tone_items, tone_item_bytes() * c->tone_item_cap));
         c->d_tone_items = c->sets[c->cur_set].d_tone_items;
         CK(dalloc(&c->d_tone_metrics, (size_t)c->tone_item_cap * 15));
@@ -749,6 +755,21 @@ extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t ch
         c->tone_wl = wlr > 32.0 ? (int)wlr : 32;
     }
     CK(cudaDeviceSynchronize());
+    return APD_OK;
+}
+
+extern "C" int apd_create(apd_ctx** out, int device, int sample_rate, int64_t chunk_samples, float height_min,
+                          int n_clips, const apd_clip_desc* descs, int max_batch_chunks)
+{
+    if (!out || !descs || n_clips <= 0 || chunk_samples <= 0 || max_batch_chunks <= 0)
+        return fail(APD_ERR_INVALID, "apd_create: bad arguments");
+    apd_ctx* c = new apd_ctx();
+    const int rc = create_ctx(c, device, sample_rate, chunk_samples, height_min, n_clips, descs, max_batch_chunks);
+    if (rc != APD_OK) {
+        const std::string msg = apd_last_error();          // apd_destroy must not lose the reason
+        apd_destroy(c);                                     // frees whatever was allocated before the failure
+        return fail(rc, msg);
+    }
     *out = c;
     return APD_OK;
 }

@@ -263,3 +263,52 @@ def test_phase2_normalised_maximum_is_exactly_one():
         assert float(buf[:n.value].max()) == 1.0, (ci, name, float(buf[:n.value].max()))
         checked += 1
     assert checked > 0
+
+
+def test_dense_candidates_overflow_is_retried_not_fatal():
+    """A 0.15 s marker-tone clip inside minutes of steady tone keeps ~N_out / L peaks per unit: more records per
+    sub-batch than the device lists hold on average.  The scan must split the range and finish (it used to
+    raise mid-stream), with the same candidates as a chunk-by-chunk scan."""
+    sr = 8000
+    t = np.arange(int(0.15 * sr)) / sr
+    beep = (0.8 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    clips = [{"name": "pip", "audio": beep, "strategy": "marker_tone",
+              "strategy_params": {"dominant_frequency_hz": 1000.0}}]
+    n = 900 * sr
+    audio = (0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(n) / sr)).astype(np.float32)
+    big = make_detector(clips, sr, 10, max_batch_chunks=90).scan_array(audio)
+    assert big.n_candidates > 4096
+    one = make_detector(clips, sr, 10, max_batch_chunks=1).scan_array(audio)
+    assert big.records.tobytes() == one.records.tobytes()
+    assert big.peak_times == one.peak_times
+
+
+def test_explicit_zero_height_is_honoured():
+    """height_min=0.0 is a value, not "unset" (reference :520 substitutes 0.25 only for None): every local maximum
+    becomes a candidate, as in the oracle."""
+    run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c4_lowheight"][0]
+    clips, audio = synthetic_inputs(run)
+    out = compare_with_oracle(clips[:2], audio[:8 * 8000], 8000, 4, height_min=0.0, max_batch_chunks=2)
+    low = compare_with_oracle(clips[:2], audio[:8 * 8000], 8000, 4, height_min=None, max_batch_chunks=2)
+    assert out["candidates"] > low["candidates"]
+
+
+def test_short_reads_are_refilled():
+    """A raw source that returns fewer bytes than asked for: the chunk is refilled, nothing is dropped."""
+    import io
+    from audio_pattern_detector_b200.audio_clip import AudioStream
+
+    class Dribble(io.RawIOBase):
+        def __init__(self, data):
+            self.b, self.k = io.BytesIO(data), 0
+
+        def read(self, n=-1):
+            self.k += 1
+            return self.b.read(min(n, 4 * (3001 + 7 * (self.k % 11))))
+
+    run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c10"][0]
+    clips, audio = synthetic_inputs(run)
+    det = make_detector(clips, 8000, 10, max_batch_chunks=3)
+    want = det.scan_array(audio)
+    times, total = det.find_clip_in_audio(AudioStream(name="s", audio_stream=Dribble(audio.tobytes()), sample_rate=8000))
+    assert times == want.peak_times and total == want.total_time
