@@ -235,6 +235,8 @@ struct apd_ctx {
     int out_capacity = 0;
     // tone
     int tone_ctas = 0, tone_wl = 0, tone_item_cap = 0;      // tone_ctas: work items per tone round
+    unsigned char* d_tone_alive = nullptr;                  // per work item: flanks still needed
+    bool tone_all_segments = false;                         // a trace / single-candidate call wants every metric
     int tone_max_P = 0, tone_max_L = 0;
     double* d_tone_stats = nullptr;
     long long tone_stride = 0;
@@ -751,6 +753,7 @@ static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_sam
         for (auto& b : used_sets(c)) CK(cudaMalloc(&b.d_tone_items, tone_item_bytes() * c->tone_item_cap));
         c->d_tone_items = c->sets[c->cur_set].d_tone_items;
         CK(dalloc(&c->d_tone_metrics, (size_t)c->tone_item_cap * 15));
+        CK(dalloc(&c->d_tone_alive, (size_t)c->tone_item_cap));
         const double wlr = std::nearbyint(0.025 * (double)sample_rate);
         c->tone_wl = wlr > 32.0 ? (int)wlr : 32;
     }
@@ -826,7 +829,7 @@ extern "C" int apd_destroy(apd_ctx* c)
                     c->d_clip_spec_off, c->d_kw_patch,
                     c->d_kw_state, c->d_kw_energy, c->d_kw_em1, c->d_scratch, c->d_corr,
                     c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->d_peaks, c->d_n_peaks, c->d_n_cands,
-                    c->d_slot_cands, c->d_tone_scratch, c->d_tone_metrics, c->d_tone_stats,
+                    c->d_slot_cands, c->d_tone_scratch, c->d_tone_metrics, c->d_tone_stats, c->d_tone_alive,
                     c->d_unit_desc};
     for (void* p : ptrs) cudaFree(p);
     delete c;
@@ -997,7 +1000,8 @@ static void phase2_tone(apd_ctx* c, int n_items, cudaStream_t st)
     VerifyArgs VA{PA, CV, c->chunk_begin, c->sr, c->d_gain, G, c->d_out, c->d_counts + S + 1, c->out_capacity,
                   c->d_slot_cands, c->d_tone_scratch, c->tone_stride, c->tone_ctas};
     launch_tone_batch(VA, c->d_tone_items, c->d_counts + S + 3, n_items, c->d_tone_metrics, c->d_tone_stats,
-                      c->tone_ctas, c->tone_max_P, c->tone_max_L, c->tone_wl, st, &c->launches);
+                      c->tone_ctas, c->tone_max_P, c->tone_max_L, c->tone_wl, c->tone_all_segments, c->d_tone_alive, st,
+                      &c->launches);
 }
 
 // Select the units that can have peaks, then run the first phase-2 round without waiting for the
@@ -1153,6 +1157,9 @@ extern "C" int apd_scan(apd_ctx* c, const float* audio, int64_t base, int64_t n,
     if (!c || !cand_host || !n_cand) return fail(APD_ERR_INVALID, "scan: null argument");
     if (ce <= cb) return fail(APD_ERR_INVALID, "scan: empty chunk range");
     CK(cudaSetDevice(c->device));
+    // with a trace every tone metric is reported; without, the flanks of candidates whose matched segment already
+    // fails are not computed (same decisions, verify.cu: k_tone_gate)
+    c->tone_all_segments = trace != nullptr || (getenv("APD_B200_TONE_ALL") && atoi(getenv("APD_B200_TONE_ALL")));
     static const bool loud_stream = !(getenv("APD_B200_LOUD_STREAM") && !atoi(getenv("APD_B200_LOUD_STREAM")));
     cudaStream_t s2 = c->side, s3 = loud_stream ? c->pre : s1;
     *n_cand = 0;
@@ -1292,6 +1299,7 @@ extern "C" int apd_verify_tone(apd_ctx* c, int32_t clip, const float* section_de
     CK(cudaMemcpyAsync(c->d_tone_items, &item, sizeof(item), cudaMemcpyHostToDevice, st));
     const int one = 1;
     CK(cudaMemcpyAsync(c->d_counts + S + 3, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    c->tone_all_segments = true;
     phase2_tone(c, 1, st);
     apd_candidate rec;
     CK(cudaMemcpyAsync(&rec, c->d_out, sizeof(rec), cudaMemcpyDeviceToHost, st));

@@ -73,9 +73,11 @@ constexpr int kMaxSlots = 1024;           // slots per phase-2 round (k_emit kee
 void launch_verify(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches);
 void launch_tone_collect(const VerifyArgs& A, int nslots, void* items, int* n_items, int item_capacity,
                          cudaStream_t st, long long* launches);
+// all_segments == false: the flank transforms of items whose matched segment already fails are skipped (their
+// metrics read as zero, the decision is unchanged); alive: n_items bytes of device scratch
 void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n_items, double* metrics,
-                       double* stats, int round_items, int max_P, int max_L, int wl, cudaStream_t st,
-                       long long* launches);
+                       double* stats, int round_items, int max_P, int max_L, int wl, bool all_segments,
+                       unsigned char* alive, cudaStream_t st, long long* launches);
 void launch_emit(const VerifyArgs& A, int nslots, cudaStream_t st, long long* launches);
 void launch_tone_tables(int L, int P, const double2* tw, double2* buf0, double2* buf1, double2* chirp_fft,
                         double2* pre, double2* post, cudaStream_t st);

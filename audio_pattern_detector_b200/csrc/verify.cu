@@ -311,7 +311,14 @@ struct ToneRound {
     double* stats;                // [(r*3+seg)*4] = {tot, band sum, detected Hz, -}
     double* metrics;              // [item][seg][5]
     int wl, hop;
+    int seg0;                     // this pass handles segments seg0 + blockIdx.{y|x}
+    const unsigned char* alive;   // flank passes: items whose matched segment failed are skipped (nullptr: none is)
 };
+
+__device__ __forceinline__ bool tone_skip(const ToneRound& T, int r, int seg)
+{
+    return r >= T.n_round || (seg > 0 && T.alive && !T.alive[T.i0 + r]);
+}
 
 __device__ __forceinline__ double2* tone_buf(const ToneRound& T, int r, int seg, int which)
 {
@@ -354,8 +361,8 @@ __device__ __forceinline__ double tone_sample(const ToneSeg& s, int k)
 __global__ void __launch_bounds__(256)
 k_tone_prep(VerifyArgs A, ToneRound T)
 {
-    const int r = blockIdx.z, seg = blockIdx.y;
-    if (r >= T.n_round) return;
+    const int r = blockIdx.z, seg = T.seg0 + blockIdx.y;
+    if (tone_skip(T, r, seg)) return;
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < s.P; n += gridDim.x * blockDim.x) {
         double2 v = make_double2(0, 0);
@@ -413,8 +420,8 @@ template <bool INV>
 __global__ void __launch_bounds__(256)
 k_tone_fft_pass(VerifyArgs A, ToneRound T, int slot)
 {
-    const int r = blockIdx.z, seg = blockIdx.y;
-    if (r >= T.n_round) return;
+    const int r = blockIdx.z, seg = T.seg0 + blockIdx.y;
+    if (tone_skip(T, r, seg)) return;
     const int clip = T.items[T.i0 + r].clip;
     const int P = A.cv.tone_P[clip];
     const int lg = 31 - __clz(P);
@@ -481,8 +488,8 @@ k_tone_fft_pass(VerifyArgs A, ToneRound T, int slot)
 __global__ void __launch_bounds__(256)
 k_tone_mul(VerifyArgs A, ToneRound T)
 {
-    const int r = blockIdx.z, seg = blockIdx.y;
-    if (r >= T.n_round) return;
+    const int r = blockIdx.z, seg = T.seg0 + blockIdx.y;
+    if (tone_skip(T, r, seg)) return;
     const int clip = T.items[T.i0 + r].clip;
     const int P = A.cv.tone_P[clip];
     double2* f = tone_buf(T, r, seg, tone_npass(P) & 1);
@@ -496,8 +503,8 @@ k_tone_stats(VerifyArgs A, ToneRound T)
 {
     __shared__ double red[32];
     __shared__ int s_arg;
-    const int r = blockIdx.y, seg = blockIdx.x;
-    if (r >= T.n_round) return;
+    const int r = blockIdx.y, seg = T.seg0 + blockIdx.x;
+    if (tone_skip(T, r, seg)) return;
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
     const double2* __restrict__ c = tone_buf(T, r, seg, 0);
     const double2* __restrict__ post = A.cv.tone_post[s.clip];
@@ -545,8 +552,8 @@ __global__ void __launch_bounds__(256)
 k_tone_frames(VerifyArgs A, ToneRound T)
 {
     extern __shared__ double2 ftw[];            // e^{-2 pi i t / wl} (t < wl), the frame Hann window (.x), then samples
-    const int r = blockIdx.z, seg = blockIdx.y;
-    if (r >= T.n_round) return;
+    const int r = blockIdx.z, seg = T.seg0 + blockIdx.y;
+    if (tone_skip(T, r, seg)) return;
     if (T.stats[((long long)r * 3 + seg) * 4] == 0.0) return;                 // du.py:65-72
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
     const int wl = T.wl, hop = T.hop;
@@ -588,8 +595,8 @@ k_tone_frames(VerifyArgs A, ToneRound T)
 __global__ void __launch_bounds__(128)
 k_tone_frame_stats(VerifyArgs A, ToneRound T)
 {
-    const int r = blockIdx.z, seg = blockIdx.y;
-    if (r >= T.n_round) return;
+    const int r = blockIdx.z, seg = T.seg0 + blockIdx.y;
+    if (tone_skip(T, r, seg)) return;
     if (T.stats[((long long)r * 3 + seg) * 4] == 0.0) return;
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
     const int wl = T.wl, hop = T.hop;
@@ -620,11 +627,13 @@ k_tone_frame_stats(VerifyArgs A, ToneRound T)
 }
 
 // Thread per (item, segment): run-length summary over frames (du.py:106-117) and the 5 metrics.
-__global__ void k_tone_final(VerifyArgs A, ToneRound T)
+__global__ void k_tone_final(VerifyArgs A, ToneRound T, int nseg)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T.n_round * 3) return;
-    const int r = t / 3, seg = t % 3;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= T.n_round * nseg) return;
+    const int r = t0 / nseg, seg = T.seg0 + t0 % nseg;
+    if (tone_skip(T, r, seg)) return;
+    const int t = r * 3 + seg;
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
     const double* st = T.stats + (long long)t * 4;
     const double tot = st[0];
@@ -654,6 +663,25 @@ __global__ void k_tone_final(VerifyArgs A, ToneRound T)
     out[4] = meanp;
 }
 
+// The conditions of apd.py:707-724 that only look at the matched segment (frequency within 5 %, band purity, active
+// frame ratio, longest run, mean active purity); the flank purities complete the decision.
+__device__ __forceinline__ bool tone_match_ok(const double* m, const double* th, double f0)
+{
+    bool ok = fabs(m[0] - f0) <= fmax(0.05 * fmax(fabs(m[0]), fabs(f0)), 0.0);   // apd.py:707
+    return ok && m[1] >= th[0] && m[2] >= th[1] && (long long)m[3] >= (long long)th[2] && m[4] >= th[3];
+}
+
+// After the matched-segment pass of a round: which of its items still need their flanks.  A candidate whose matched
+// segment fails is rejected whatever its flanks are (the decision is a conjunction), so unless every metric was asked
+// for (trace / single-candidate calls) the two flank transforms of such items are not computed and read as zero.
+__global__ void k_tone_gate(VerifyArgs A, ToneRound T, unsigned char* alive)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= T.n_round) return;
+    const int clip = T.items[T.i0 + r].clip;
+    alive[T.i0 + r] = tone_match_ok(T.metrics + (long long)(T.i0 + r) * 15, A.cv.tone_thr + clip * 6, A.cv.tone_hz[clip]) ? 1 : 0;
+}
+
 // Decision (apd.py:707-724) and record emission for the deferred tone candidates.
 __global__ void k_tone_decide(VerifyArgs A, const ToneItem* __restrict__ items, const int* __restrict__ n_items,
                               const double* __restrict__ metrics)
@@ -677,9 +705,7 @@ __global__ void k_tone_decide(VerifyArgs A, const ToneItem* __restrict__ items, 
         const double* th = A.cv.tone_thr + clip * 6;
         const double f0 = A.cv.tone_hz[clip];
         const double lo = fmin(m[5 + 1], m[10 + 1]), hi = fmax(m[5 + 1], m[10 + 1]);
-        bool ok = fabs(m[0] - f0) <= fmax(0.05 * fmax(fabs(m[0]), fabs(f0)), 0.0);   // apd.py:707
-        ok = ok && m[1] >= th[0] && m[2] >= th[1] && (long long)m[3] >= (long long)th[2] && m[4] >= th[3]
-                && lo <= th[4] && hi <= th[5];                                         // apd.py:717-724
+        const bool ok = tone_match_ok(m, th, f0) && lo <= th[4] && hi <= th[5];       // apd.py:717-724
         if (ok) rec.flags |= APD_FLAG_ACCEPT;
     }
     const int o = atomicAdd(A.out_count, 1);
@@ -754,8 +780,8 @@ void launch_tone_collect(const VerifyArgs& A, int nslots, void* items, int* n_it
 }
 
 void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n_items, double* metrics,
-                       double* stats, int round_items, int max_P, int max_L, int wl, cudaStream_t st,
-                       long long* launches)
+                       double* stats, int round_items, int max_P, int max_L, int wl, bool all_segments,
+                       unsigned char* alive, cudaStream_t st, long long* launches)
 {
     if (n_items <= 0 || round_items <= 0) return;
     static bool attr = false;
@@ -770,27 +796,39 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
     const int hop = wl / 2 > 1 ? wl / 2 : 1;
     const int nf_max = max_L - wl > 0 ? (max_L - wl + hop - 1) / hop : 0;
     const long long work_max = (long long)nf_max * (wl / 2 + 1);
+    // skipped flank segments read as zero
+    cudaMemsetAsync(metrics, 0, sizeof(double) * 15 * (size_t)n_items, st);
     for (int i0 = 0; i0 < n_items; i0 += round_items) {
         ToneRound T{(const ToneItem*)items, i0, std::min(round_items, n_items - i0), A.tone_scratch,
-                    A.tone_scratch_stride, stats, metrics, wl, hop};
+                    A.tone_scratch_stride, stats, metrics, wl, hop, 0, nullptr};
         const unsigned R = (unsigned)T.n_round;
         // grid-stride in x (capping the grid at 32 CTAs per transform was measured: no gain for the correlate stage
         // that shares the GPU, longer phase 2)
         const unsigned gx = (unsigned)((max_P / 4 + 255) / 256);
-        k_tone_prep<<<dim3(gx, 3, R), 256, 0, st>>>(A, T);
-        for (int s = 0; s < max_pass; ++s)
-            k_tone_fft_pass<false><<<dim3(gx, 3, R), 256, 0, st>>>(A, T, s);
-        k_tone_mul<<<dim3(gx, 3, R), 256, 0, st>>>(A, T);
-        for (int s = 0; s < max_pass; ++s)
-            k_tone_fft_pass<true><<<dim3(gx, 3, R), 256, 0, st>>>(A, T, s);
-        k_tone_stats<<<dim3(3, R), 1024, 0, st>>>(A, T);
-        if (work_max > 0) {
-            k_tone_frames<<<dim3((unsigned)((nf_max + kFramesPerCta - 1) / kFramesPerCta), 3, R), 256,
-                            (size_t)2 * wl * sizeof(double2) + (size_t)kFramesPerCta * wl * sizeof(double), st>>>(A, T);
-            k_tone_frame_stats<<<dim3((nf_max + 127) / 128, 3, R), 128, 0, st>>>(A, T);
+        // pass 0: the matched segment of every item; pass 1: the two flanks of the items that still need them
+        for (int pass = 0; pass < 2; ++pass) {
+            const unsigned ns = pass == 0 ? 1u : 2u;
+            T.seg0 = pass;
+            T.alive = (pass == 1 && !all_segments) ? alive : nullptr;
+            k_tone_prep<<<dim3(gx, ns, R), 256, 0, st>>>(A, T);
+            for (int s = 0; s < max_pass; ++s)
+                k_tone_fft_pass<false><<<dim3(gx, ns, R), 256, 0, st>>>(A, T, s);
+            k_tone_mul<<<dim3(gx, ns, R), 256, 0, st>>>(A, T);
+            for (int s = 0; s < max_pass; ++s)
+                k_tone_fft_pass<true><<<dim3(gx, ns, R), 256, 0, st>>>(A, T, s);
+            k_tone_stats<<<dim3(ns, R), 1024, 0, st>>>(A, T);
+            if (work_max > 0) {
+                k_tone_frames<<<dim3((unsigned)((nf_max + kFramesPerCta - 1) / kFramesPerCta), ns, R), 256,
+                                (size_t)2 * wl * sizeof(double2) + (size_t)kFramesPerCta * wl * sizeof(double), st>>>(A, T);
+                k_tone_frame_stats<<<dim3((nf_max + 127) / 128, ns, R), 128, 0, st>>>(A, T);
+            }
+            k_tone_final<<<(T.n_round * (int)ns + 63) / 64, 64, 0, st>>>(A, T, (int)ns);
+            *launches += 5 + 2 * max_pass + (work_max > 0 ? 2 : 0);
+            if (pass == 0 && !all_segments) {
+                k_tone_gate<<<(T.n_round + 63) / 64, 64, 0, st>>>(A, T, alive);
+                ++*launches;
+            }
         }
-        k_tone_final<<<(T.n_round * 3 + 63) / 64, 64, 0, st>>>(A, T);
-        *launches += 5 + 2 * max_pass + (work_max > 0 ? 2 : 0);
     }
     k_tone_decide<<<(n_items + 127) / 128, 128, 0, st>>>(A, (const ToneItem*)items, n_items_dev, metrics);
     ++*launches;
