@@ -437,9 +437,7 @@ template <class S, bool WRITE, int NS = WRITE ? 1 : ColStages<S>::value>
 static void launch_cols(const CUtensorMap& map, const UnitDesc* D, int nunits, int per, int M, const InvOut& out, dim3 grid,
                         cudaStream_t st)
 {
-    // APD_B200_COLS_PAD_KB: occupancy experiment only (extra dynamic shared memory lowers the CTAs per SM)
-    static const size_t pad = (size_t)env_int2("APD_B200_COLS_PAD_KB", 0) * 1024;
-    const size_t smem = (size_t)(2 + NS) * S::N * kTB * sizeof(c2) + ColLayout<kTB>::ALIGN + pad;
+    constexpr size_t smem = (size_t)(2 + NS) * S::N * kTB * sizeof(c2) + ColLayout<kTB>::ALIGN;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_corr_cols<S, WRITE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
