@@ -626,12 +626,15 @@ k_tone_frame_stats(VerifyArgs A, ToneRound T)
     fact[f] = (fabs(fdom - s.f0) <= tol && pur >= 0.55) ? 1 : 0;              // du.py:102-105
 }
 
-// Thread per (item, segment): run-length summary over frames (du.py:106-117) and the 5 metrics.
-__global__ void k_tone_final(VerifyArgs A, ToneRound T, int nseg)
+// Warp per (item, segment): run-length summary over frames (du.py:106-117) and the 5 metrics.  Each lane summarises a
+// contiguous slice of the frames (count, active count, purity sum, longest run, leading / trailing run, all-active
+// flag); lane 0 chains the 32 slices.
+__global__ void __launch_bounds__(128)
+k_tone_final(VerifyArgs A, ToneRound T, int nseg)
 {
-    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t0 >= T.n_round * nseg) return;
-    const int r = t0 / nseg, seg = T.seg0 + t0 % nseg;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= T.n_round * nseg) return;
+    const int r = w / nseg, seg = T.seg0 + w % nseg;
     if (tone_skip(T, r, seg)) return;
     const int t = r * 3 + seg;
     const ToneSeg s = tone_seg(A, T.items[T.i0 + r], seg);
@@ -643,24 +646,49 @@ __global__ void k_tone_final(VerifyArgs A, ToneRound T, int nseg)
     const unsigned char* fact = (const unsigned char*)(fpur + nf);
     double ratio = 0, meanp = 0;
     int longest = 0;
-    if (tot != 0.0) {
-        int frames = 0, active = 0, run = 0;
+    if (tot != 0.0) {                                                          // warp-uniform
+        const int per = (nf + 31) / 32, f0 = lane * per, f1 = min(nf, f0 + per);
+        int frames = 0, active = 0, run = 0, best = 0, lead = 0;
+        bool all_active = true;                                                // every frame of the slice extends a run
         double psum = 0;
-        for (int f = 0; f < nf; ++f) {
-            if (fpur[f] < 0.0) { run = 0; continue; }
-            ++frames;
-            if (fact[f]) { ++active; ++run; longest = run > longest ? run : longest; psum += fpur[f]; }
-            else run = 0;
+        for (int f = f0; f < f1; ++f) {
+            const double pu = fpur[f];
+            const bool on = pu >= 0.0 && fact[f];
+            if (pu >= 0.0) ++frames;
+            if (on) { ++active; ++run; best = max(best, run); psum += pu; }
+            else { if (all_active) lead = run; all_active = false; run = 0; }
+        }
+        if (all_active) lead = run;
+        const int trail = run;
+        const int len = max(f1 - f0, 0);
+        // totals
+        for (int o = 16; o > 0; o >>= 1) {
+            frames += __shfl_xor_sync(0xffffffffu, frames, o);
+            active += __shfl_xor_sync(0xffffffffu, active, o);
+            psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        }
+        // longest run across slice boundaries: lane 0 walks the slices in order
+        int carry = 0;
+        longest = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int b = __shfl_sync(0xffffffffu, best, l), ld = __shfl_sync(0xffffffffu, lead, l);
+            const int tr = __shfl_sync(0xffffffffu, trail, l), ln = __shfl_sync(0xffffffffu, len, l);
+            const int aa = __shfl_sync(0xffffffffu, all_active ? 1 : 0, l);
+            if (ln == 0) continue;
+            longest = max(longest, max(b, carry + ld));
+            carry = aa ? carry + ln : tr;
         }
         ratio = frames > 0 ? (double)active / (double)frames : 0.0;
         meanp = active > 0 ? psum / (double)active : 0.0;
     }
-    double* out = T.metrics + ((long long)(T.i0 + r) * 3 + seg) * 5;
-    out[0] = st[2];
-    out[1] = tot != 0.0 ? st[1] / tot : 0.0;                                  // du.py:64-75
-    out[2] = ratio;
-    out[3] = (double)longest;
-    out[4] = meanp;
+    if (lane == 0) {
+        double* out = T.metrics + ((long long)(T.i0 + r) * 3 + seg) * 5;
+        out[0] = st[2];
+        out[1] = tot != 0.0 ? st[1] / tot : 0.0;                               // du.py:64-75
+        out[2] = ratio;
+        out[3] = (double)longest;
+        out[4] = meanp;
+    }
 }
 
 // The conditions of apd.py:707-724 that only look at the matched segment (frequency within 5 %, band purity, active
@@ -822,7 +850,7 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
                                 (size_t)2 * wl * sizeof(double2) + (size_t)kFramesPerCta * wl * sizeof(double), st>>>(A, T);
                 k_tone_frame_stats<<<dim3((nf_max + 127) / 128, ns, R), 128, 0, st>>>(A, T);
             }
-            k_tone_final<<<(T.n_round * (int)ns + 63) / 64, 64, 0, st>>>(A, T, (int)ns);
+            k_tone_final<<<(T.n_round * (int)ns + 3) / 4, 128, 0, st>>>(A, T, (int)ns);
             *launches += 5 + 2 * max_pass + (work_max > 0 ? 2 : 0);
             if (pass == 0 && !all_segments) {
                 k_tone_gate<<<(T.n_round + 63) / 64, 64, 0, st>>>(A, T, alive);
