@@ -225,12 +225,13 @@ __device__ __forceinline__ float max_if_lt(float best, float y, int a, int b)
 // the first exchange of the current one (the input buffer is free then), i.e. two passes ahead; NS = 2: a unit ahead.
 template <class S> struct ColThreads { static constexpr int value = (2 * (S::N / 8) + 31) / 32 * 32; };   // whole warps
 
-// input tiles in flight per CTA: two (the next unit's tile is requested a whole unit ahead) where three CTAs of
-// 4 buffers still fit the SM's shared memory (N1 <= 576), else one (requested after the first exchange)
-template <class S> struct ColStages { static constexpr int value = S::N <= 576 ? 2 : 1; };
+// input tiles in flight per CTA: one (the next unit's tile is requested after the first exchange), which lets four
+// CTAs of N1 = 512 (3 x 16 KB) share an SM; two (a whole unit ahead) for N1 = 576, where a fourth CTA does not fit
+// but a fourth buffer does (measured equal to one)
+template <class S> struct ColStages { static constexpr int value = S::N == 576 ? 2 : 1; };
 
 template <class S, bool WRITE, int NS>
-__global__ void __launch_bounds__(ColThreads<S>::value, WRITE ? 2 : 3)
+__global__ void __launch_bounds__(ColThreads<S>::value, WRITE ? 2 : (S::N == 512 ? 4 : 3))
 k_corr_cols(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict__ D, int nunits, int per, int M,
             unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride)
 {
