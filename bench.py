@@ -244,7 +244,8 @@ def main() -> None:
     if world > 1:
         bind_to_gpu_numa_node(local)      # before any pinned allocation: host buffers on the GPU's own socket
         dist.init_process_group("nccl", device_id=torch.device(dev))
-        host_group = dist.new_group(backend="gloo")       # host-side gather of the detections (c5)
+        if WORKLOADS[args.workload]["scaling"] == "strong":
+            host_group = dist.new_group(backend="gloo")   # host-side gather of the detections (c5)
 
     from audio_pattern_detector_b200 import sharding
     from audio_pattern_detector_b200 import workloads as W
