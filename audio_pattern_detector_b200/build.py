@@ -17,8 +17,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
+STAMP = os.path.join(HERE, "build", "sources.sha256")
+
+
 def _newer(a: str, b: str) -> bool:
     return not os.path.exists(b) or os.path.getmtime(a) > os.path.getmtime(b)
+
+
+def _fingerprint(files: list[str]) -> str:
+    """Content hash of every source, header and compile flag: an in-tree .so built from other sources is never reused
+    silently, whatever the file times say (a checkout or a copy can reset them)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(files):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -27,6 +42,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "apd_b200.h"))
+    fp = _fingerprint([os.path.join(CSRC, src) for src in SOURCES] + headers)
+    try:
+        with open(STAMP) as fh:
+            stale = fh.read().strip() != fp
+    except OSError:
+        stale = True                      # no record of what the objects were built from
+    force = force or stale
     objs = []
     relink = force
     procs = []
@@ -51,6 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         # -cudart shared: the library binds to the libcudart.so.12 of the image instead of carrying a private static copy
         subprocess.run([nvcc, "-shared", "-cudart", "shared", "-o", LIB, *objs, "-gencode",
                         "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"], check=True)
+        with open(STAMP, "w") as fh:
+            fh.write(fp + "\n")
     return LIB
 
 

@@ -56,3 +56,16 @@ def test_errors_without_a_device_are_loud():
     ctx = ctypes.c_void_p()
     rc = L.apd_create(ctypes.byref(ctx), 0, 8000, 16000, 0.0, 1, d, 1)
     assert rc != 0 and L.apd_last_error()
+
+
+def test_build_is_stamped_with_a_content_hash_of_its_sources():
+    """A stale in-tree .so is never reused silently: build.py records the hash of every source, header and flag it
+    compiled and rebuilds when they differ."""
+    import os
+    from audio_pattern_detector_b200 import build as b
+    headers = [os.path.join(b.CSRC, f) for f in os.listdir(b.CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(os.path.dirname(b.HERE), "include", "apd_b200.h"))
+    fp = b._fingerprint([os.path.join(b.CSRC, s) for s in b.SOURCES] + headers)
+    b.build()
+    with open(b.STAMP) as fh:
+        assert fh.read().strip() == fp

@@ -312,3 +312,19 @@ def test_short_reads_are_refilled():
     want = det.scan_array(audio)
     times, total = det.find_clip_in_audio(AudioStream(name="s", audio_stream=Dribble(audio.tobytes()), sample_rate=8000))
     assert times == want.peak_times and total == want.total_time
+
+
+def test_sharded_archive_generator_is_world_size_independent():
+    """bench.py --workload c5: every rank generates its slab of ONE logical stream; any cut gives the same samples."""
+    import torch
+    from audio_pattern_detector_b200 import workloads as W
+    sr, spc = 8000, 60
+    pats = W.make_patterns(8, sr, seed=1)
+    secs = 1500.0                                   # 12 M samples: three noise blocks, plants across block borders
+    full, plants = W.make_stream_slab_device(secs, pats, sr, 0, 4, spc, 0, int(secs * sr), device="cuda")
+    assert len(plants) > 0
+    n = full.numel()
+    for lo, hi in ((0, n // 3), (n // 3 - 80000, 2 * n // 3), (4194304 - 17, 4194304 + 900001), (n - 123457, n)):
+        part, plants2 = W.make_stream_slab_device(secs, pats, sr, 0, 4, spc, lo, hi, device="cuda")
+        assert plants2 == plants
+        assert torch.equal(part, full[lo:hi])
