@@ -328,3 +328,23 @@ def test_sharded_archive_generator_is_world_size_independent():
         part, plants2 = W.make_stream_slab_device(secs, pats, sr, 0, 4, spc, lo, hi, device="cuda")
         assert plants2 == plants
         assert torch.equal(part, full[lo:hi])
+
+
+def test_tone_flank_gate_does_not_change_decisions():
+    """Without a trace the flank transforms of tone candidates whose matched segment already fails are skipped
+    (verify.cu: k_tone_gate); the accept decisions, timestamps and the matched-segment metrics are those of the full
+    computation, and the flank metrics of the survivors are untouched."""
+    run = [r for r in FIXTURE_RUNS if r["wav"].endswith("radio1_2026-04-06_12_to_13_28m49_opening.wav") and r["sr"] == 8000][0]
+    clips, audio = fixture_clips(run), fixture_audio(run)
+    full = make_detector(clips, 8000, 60).scan_array(audio, collect_trace=True)
+    fast = make_detector(clips, 8000, 60).scan_array(audio)
+    assert fast.peak_times == full.peak_times and fast.events == full.events
+    a, b = full.records, fast.records
+    assert a.shape == b.shape and (a["flags"] == b["flags"]).all() and (a["peak"] == b["peak"]).all()
+    tone = (a["flags"] >> 2) == 2
+    assert tone.any()
+    assert np.array_equal(a["tone"][tone][:, 0, :], b["tone"][tone][:, 0, :])
+    kept = tone & ((b["tone"][:, 1, :] != 0).any(axis=1) | (b["tone"][:, 2, :] != 0).any(axis=1))
+    assert np.array_equal(a["tone"][kept], b["tone"][kept])
+    accepted = tone & ((a["flags"] & 1) != 0)
+    assert accepted.any() and not (accepted & ~kept).any()
