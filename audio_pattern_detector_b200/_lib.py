@@ -65,6 +65,7 @@ PROTOTYPES: dict[str, tuple[Any, list[Any]]] = {
     "apd_resample": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                C.c_void_p, C.c_int64, C.c_void_p]),
     "apd_launch_count": (C.c_int64, [C.c_void_p]),
+    "apd_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "apd_unit_n_out": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int32)]),
 }
 

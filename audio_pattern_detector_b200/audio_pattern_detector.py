@@ -336,6 +336,12 @@ class AudioPatternDetector:
     def launch_count(self) -> int:
         return int(_lib.lib().apd_launch_count(self._ctx))
 
+    def work_counters(self, reset: bool = True) -> dict[str, int]:
+        """Phase-2 work since the last reset (what the write-back inverse, find_peaks and the verifiers ran on)."""
+        out = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().apd_work_counters(self._ctx, out, 1 if reset else 0), "apd_work_counters")
+        return dict(zip(("selected_units", "candidate_records", "tone_items", "sub_batches"), (int(v) for v in out)))
+
     def unit_n_out(self, chunk: int, clip_index: int, total_samples: int) -> int:
         n = C.c_int32()
         _lib.check(_lib.lib().apd_unit_n_out(self._ctx, chunk, clip_index, total_samples, C.byref(n)), "unit_n_out")

@@ -291,6 +291,7 @@ struct apd_ctx {
     bool profile = false;
     cudaEvent_t* ev = nullptr;
     double stage_ms[4] = {0, 0, 0, 0};
+    long long work[4] = {0, 0, 0, 0};     // selected units, candidate records, tone work items, sub-batches
 
     // state of the staged batch
     const float* audio = nullptr;
@@ -963,16 +964,21 @@ static void phase2_round(apd_ctx* c, int slot0, cudaStream_t st)
     const int ns = c->n_slots;
     const UnitCtx X = unit_ctx(c);
     InvOut O{c->d_unit_max, c->n_clips, c->d_corr, c->corr_stride, c->d_self_max};
+    // timing experiments: 0 = selection only, 1 = + write-back inverse, 2 = + find_peaks, 3+ = everything
+    static const int level = getenv("APD_B200_P2_LEVEL") ? atoi(getenv("APD_B200_P2_LEVEL")) : 9;
+    if (level < 1) return;
     for (int s = 0; s < S; ++s) {
         UnitSrc U{c->d_sel, c->d_counts + s, nullptr, 0, slot0, 0, 0, 0};
         launch_inverse(c->shapes[s].plan, X, c->d_spec, c->spec_slab, U, ns, c->d_scratch2, c->d_unit_desc2, O, true, st);
         c->launches += 3;
     }
+    if (level < 2) return;
     PeakArgs PA{c->d_sel, c->d_counts + S, slot0, c->d_geoms, c->d_clip_group, c->d_clip_len, c->height,
                 c->d_corr, c->corr_stride, c->d_cand_idx, c->d_cand_val, c->d_cand_state, c->cand_stride,
                 c->d_peaks, c->d_peak_height, c->peak_stride, c->d_n_peaks, c->d_n_cands, c->d_counts + S + 2};
     launch_find_peaks(PA, ns, st);
     ++c->launches;
+    if (level < 3) return;
     ClipVerify CV{c->d_clip_len, c->d_clip_group, c->d_strategy, c->d_self_corr_ptrs, c->d_win_lo,
                   c->d_win_hi, c->d_win_ds, c->d_win_cache_ptrs, c->d_is_short, c->d_tone_hz, c->d_tone_thr,
                   c->d_tone_P, c->d_tone_chirp_ptrs, c->d_tone_tw_ptrs, c->d_tone_pre_ptrs, c->d_tone_post_ptrs};
@@ -1076,6 +1082,10 @@ static int collect_begin(apd_ctx* c, cudaStream_t st)
     static const bool tone_low = !(getenv("APD_B200_TONE_LOW") && !atoi(getenv("APD_B200_TONE_LOW")));
     cudaStream_t ts = (tone_low && st == c->side) ? c->tone : st;
     const int n_tone = skip_tone ? 0 : c->h_counts[S + 3];
+    c->work[0] += c->h_counts[S];
+    c->work[1] += c->h_counts[S + 1] + n_tone;
+    c->work[2] += n_tone;
+    c->work[3] += 1;
     if (n_tone > 0) phase2_tone(c, n_tone, ts);
     if (c->profile) cudaEventRecord(c->ev[6], ts);
     set.n_expected = std::min(c->h_counts[S + 1] + n_tone, c->out_capacity);
@@ -1331,6 +1341,16 @@ extern "C" int apd_profile_read(apd_ctx* c, double* ms4, int reset)
     for (int i = 0; i < 4; ++i) {
         ms4[i] = c->stage_ms[i];
         if (reset) c->stage_ms[i] = 0.0;
+    }
+    return APD_OK;
+}
+
+extern "C" int apd_work_counters(apd_ctx* c, int64_t* out4, int reset)
+{
+    if (!c || !out4) return fail(APD_ERR_INVALID, "apd_work_counters: bad arguments");
+    for (int i = 0; i < 4; ++i) {
+        out4[i] = c->work[i];
+        if (reset) c->work[i] = 0;
     }
     return APD_OK;
 }

@@ -42,7 +42,29 @@ __device__ __forceinline__ void kw_step(const double* cf, double x, double& s1, 
     h2 = cf[8] * u - cf[11] * v;
 }
 
-// PASS 0: zero-state run, writes end state into state[sec][cell][4].
+// Staging of a CTA's samples into tile[cell][cells + 1 pad]: 4-byte asynchronous copies, so that all of a thread's
+// loads are in flight at once (a plain load -> store loop exposed one DRAM latency per element and made both passes
+// latency-bound at a tenth of the FP64 rate).
+__device__ __forceinline__ void stage_cells(float* tile, const float* __restrict__ x, int cnt, int cell)
+{
+    const int ld = cell + 1;
+    int row = 0, col = threadIdx.x;
+    while (col >= cell) { col -= cell; ++row; }
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * (unsigned)(row * ld + col)),
+                     "l"(x + i) : "memory");
+        col += blockDim.x;
+        while (col >= cell) { col -= cell; ++row; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+}
+
+// PASS 0: zero-state run, writes end state into state[sec][cell][4].  The end state of a zero-state run is linear
+//         in the samples: z = sum_t x_t g[len-1-t], g[j] = the state j samples after a unit impulse (K.imp holds g
+//         reversed).  Four independent accumulators instead of the serial recurrence.
 // PASS 1: run from state[sec][cell] (carry-in), writes energy[sec][cell]
 //         (and energy_m1[sec] = energy of the last cell without its final sample).
 template <int PASS>
@@ -60,28 +82,39 @@ k_kw_cells(KwConfig K, SectionGeom G, int cells_stride, double* __restrict__ sta
     const long long s0 = (long long)first * cell;           // first sample (section relative)
     if (s0 >= n) return;
     const int cnt = (int)min((long long)blockDim.x * cell, (long long)n - s0);
-    const float* __restrict__ x = G.audio + (start - G.base) + s0;
     const int ld = cell + 1;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) tile[(i / cell) * ld + (i % cell)] = x[i];
-    __syncthreads();
+    stage_cells(tile, G.audio + (start - G.base) + s0, cnt, cell);
     const int ci = first + threadIdx.x;
     const int lo = threadIdx.x * cell;
     if (lo >= cnt) return;
     const int len = min(cell, cnt - lo);
     const long long slot = ((long long)sec * cells_stride + ci);
-    double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v;
-    if (PASS == 1) {
-        s1 = state[slot * 4 + 0]; s2 = state[slot * 4 + 1]; h1 = state[slot * 4 + 2]; h2 = state[slot * 4 + 3];
-    }
     const float* row = tile + threadIdx.x * ld;
-    double e = 0, e_prev = 0;
-    for (int t = 0; t < len; ++t) {
-        kw_step(K.cf, (double)row[t], s1, s2, h1, h2, v);
-        if (PASS == 1) { e_prev = e; e += v * v; }
-    }
     if (PASS == 0) {
-        state[slot * 4 + 0] = s1; state[slot * 4 + 1] = s2; state[slot * 4 + 2] = h1; state[slot * 4 + 3] = h2;
+        const double2* __restrict__ g = reinterpret_cast<const double2*>(K.imp) + (size_t)(cell - len) * 2;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+        for (int t = 0; t < len; ++t) {
+            const double xd = (double)row[t];
+            const double2 g01 = __ldg(g + 2 * t), g23 = __ldg(g + 2 * t + 1);
+            a0 = fma(xd, g01.x, a0);
+            a1 = fma(xd, g01.y, a1);
+            a2 = fma(xd, g23.x, a2);
+            a3 = fma(xd, g23.y, a3);
+        }
+        double2* sp = reinterpret_cast<double2*>(state + slot * 4);
+        sp[0] = make_double2(a0, a1);
+        sp[1] = make_double2(a2, a3);
     } else {
+        const double2* sp = reinterpret_cast<const double2*>(state + slot * 4);
+        const double2 c01 = sp[0], c23 = sp[1];
+        double s1 = c01.x, s2 = c01.y, h1 = c23.x, h2 = c23.y, v;
+        double e = 0, e_prev = 0;
+        for (int t = 0; t < len; ++t) {
+            kw_step(K.cf, (double)row[t], s1, s2, h1, h2, v);
+            e_prev = e;
+            e += v * v;
+        }
         energy[slot] = e;
         if ((long long)ci * cell + len == n) energy_m1[sec] = e_prev;
     }
@@ -405,6 +438,28 @@ bool kw_config_create(int sample_rate, KwConfig* out, std::string* err)
                 for (int q = 0; q < 4; ++q) acc += pw[(p - 1) * 16 + r * 4 + q] * Mc[q * 4 + c];
                 pw[p * 16 + r * 4 + c] = acc;
             }
+    // g[j] = state j samples after a unit impulse into the zero state; stored reversed: imp[t] = g[cell - 1 - t]
+    const size_t imp_off = pw.size();
+    pw.resize(imp_off + (size_t)K.cell * 4);
+    {
+        const double* cf = K.cf;
+        double s[4];
+        const double u0 = cf[0], v0 = cf[6] * u0;
+        s[0] = cf[1] - cf[4] * u0;
+        s[1] = cf[2] - cf[5] * u0;
+        s[2] = cf[7] * u0 - cf[10] * v0;
+        s[3] = cf[8] * u0 - cf[11] * v0;
+        for (int j = 0; j < K.cell; ++j) {
+            for (int r = 0; r < 4; ++r) pw[imp_off + (size_t)(K.cell - 1 - j) * 4 + r] = s[r];
+            const double u = s[0];
+            const double n1 = -cf[4] * u + s[1];
+            const double n2 = -cf[5] * u;
+            const double v = cf[6] * u + s[2];
+            const double n3 = cf[7] * u - cf[10] * v + s[3];
+            const double n4 = cf[8] * u - cf[11] * v;
+            s[0] = n1; s[1] = n2; s[2] = n3; s[3] = n4;
+        }
+    }
     double* d = nullptr;
     if (cudaMalloc(&d, pw.size() * sizeof(double)) != cudaSuccess ||
         cudaMemcpy(d, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -412,6 +467,7 @@ bool kw_config_create(int sample_rate, KwConfig* out, std::string* err)
         return false;
     }
     K.mpow = d;
+    K.imp = d + imp_off;
     *out = K;
     return true;
 }
@@ -420,6 +476,7 @@ void kw_config_destroy(KwConfig* K)
 {
     if (K->mpow) cudaFree((void*)K->mpow);
     K->mpow = nullptr;
+    K->imp = nullptr;
 }
 
 void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom* h_geoms,

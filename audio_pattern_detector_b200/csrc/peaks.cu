@@ -68,32 +68,53 @@ k_find_peaks(PeakArgs A)
     unsigned char* state = A.cand_state + (long long)slot * A.cand_stride;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
-    // ---- 1. local maxima >= height, ordered (each thread owns kPeakItems consecutive samples)
+    // ---- 1. local maxima >= height, ordered (each thread owns kPeakItems consecutive samples of a tile).
+    //         The ten samples a thread needs are loaded up front (two 16-byte loads + the two neighbours), and a
+    //         tile without any candidate - nearly all of them - costs one barrier and no scan.
     int base = 0;
-    for (int t0 = 1; t0 < n - 1; t0 += blockDim.x * kPeakItems) {
+    const bool vec_ok = (reinterpret_cast<unsigned long long>(q) & 15ull) == 0ull;
+    for (int t0 = 0; t0 < n - 1; t0 += blockDim.x * kPeakItems) {
         const int i0 = t0 + threadIdx.x * kPeakItems;
         int pidx[kPeakItems];
         float pval[kPeakItems];
         int cnt = 0;
         if (i0 < n - 1) {
-            float prev = q[i0 - 1];
+            float w[kPeakItems + 2];                         // w[k + 1] = q[i0 + k], k = -1 .. kPeakItems
+            if (vec_ok && i0 + kPeakItems < n) {
+                const float4 a = *reinterpret_cast<const float4*>(q + i0);
+                const float4 b = *reinterpret_cast<const float4*>(q + i0 + 4);
+                w[0] = i0 > 0 ? q[i0 - 1] : 0.0f;
+                w[kPeakItems + 1] = q[i0 + kPeakItems];
+                w[1] = a.x; w[2] = a.y; w[3] = a.z; w[4] = a.w;
+                w[5] = b.x; w[6] = b.y; w[7] = b.z; w[8] = b.w;
+            } else {
 #pragma unroll
-            for (int k = 0; k < kPeakItems; ++k) {
-                const int i = i0 + k;
-                if (i >= n - 1) break;
-                const float v = q[i];
-                if (prev < v) {
-                    int e = i;
-                    while (e + 1 < n && q[e + 1] == v) ++e;
-                    if (e + 1 < n && v > q[e + 1] && v >= A.height) {
-                        pidx[cnt] = (i + e) >> 1;
-                        pval[cnt] = v;
-                        ++cnt;
+                for (int k = 0; k < kPeakItems + 2; ++k) {
+                    const int idx = i0 + k - 1;
+                    w[k] = (idx >= 0 && idx < n) ? q[idx] : 0.0f;
+                }
+            }
+            float hi = w[1];
+#pragma unroll
+            for (int k = 2; k <= kPeakItems; ++k) hi = fmaxf(hi, w[k]);
+            if (hi >= A.height) {
+#pragma unroll
+                for (int k = 0; k < kPeakItems; ++k) {
+                    const int i = i0 + k;
+                    const float v = w[k + 1];
+                    if (i >= 1 && i < n - 1 && w[k] < v && v >= A.height) {
+                        if (w[k + 2] != v) {
+                            if (v > w[k + 2]) { pidx[cnt] = i; pval[cnt] = v; ++cnt; }
+                        } else {
+                            int e = i + 1;                   // plateau: walk to its end in memory
+                            while (e + 1 < n && q[e + 1] == v) ++e;
+                            if (e + 1 < n && v > q[e + 1]) { pidx[cnt] = (i + e) >> 1; pval[cnt] = v; ++cnt; }
+                        }
                     }
                 }
-                prev = v;
             }
         }
+        if (!__syncthreads_or(cnt)) continue;
         int tot;
         const int off = base + block_exscan(cnt, warp_tot, &tot);
         for (int k = 0; k < cnt; ++k) {

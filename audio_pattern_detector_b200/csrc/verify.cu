@@ -313,6 +313,7 @@ struct ToneRound {
     int wl, hop;
     int seg0;                     // this pass handles segments seg0 + blockIdx.{y|x}
     const unsigned char* alive;   // flank passes: items whose matched segment failed are skipped (nullptr: none is)
+    int frames;                   // 0: this pass computes no STFT frame metrics (they read as zero)
 };
 
 __device__ __forceinline__ bool tone_skip(const ToneRound& T, int r, int seg)
@@ -646,7 +647,7 @@ k_tone_final(VerifyArgs A, ToneRound T, int nseg)
     const unsigned char* fact = (const unsigned char*)(fpur + nf);
     double ratio = 0, meanp = 0;
     int longest = 0;
-    if (tot != 0.0) {                                                          // warp-uniform
+    if (tot != 0.0 && T.frames) {                                              // warp-uniform
         const int per = (nf + 31) / 32, f0 = lane * per, f1 = min(nf, f0 + per);
         int frames = 0, active = 0, run = 0, best = 0, lead = 0;
         bool all_active = true;                                                // every frame of the slice extends a run
@@ -828,16 +829,22 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
     cudaMemsetAsync(metrics, 0, sizeof(double) * 15 * (size_t)n_items, st);
     for (int i0 = 0; i0 < n_items; i0 += round_items) {
         ToneRound T{(const ToneItem*)items, i0, std::min(round_items, n_items - i0), A.tone_scratch,
-                    A.tone_scratch_stride, stats, metrics, wl, hop, 0, nullptr};
+                    A.tone_scratch_stride, stats, metrics, wl, hop, 0, nullptr, 1};
         const unsigned R = (unsigned)T.n_round;
         // grid-stride in x (capping the grid at 32 CTAs per transform was measured: no gain for the correlate stage
         // that shares the GPU, longer phase 2)
         const unsigned gx = (unsigned)((max_P / 4 + 255) / 256);
         // pass 0: the matched segment of every item; pass 1: the two flanks of the items that still need them
+        // timing experiments only (results are wrong with parts switched off): bit 0 spectrum, 1 frames, 2 summary
+        static const int parts = getenv("APD_B200_TONE_PARTS") ? atoi(getenv("APD_B200_TONE_PARTS")) : 7;
         for (int pass = 0; pass < 2; ++pass) {
             const unsigned ns = pass == 0 ? 1u : 2u;
             T.seg0 = pass;
             T.alive = (pass == 1 && !all_segments) ? alive : nullptr;
+            // the decision reads only the band purity of the flanks (apd.py:716-724): their frame metrics are
+            // computed only when every metric was asked for
+            T.frames = (pass == 0 || all_segments) ? 1 : 0;
+            if (parts & 1) {
             k_tone_prep<<<dim3(gx, ns, R), 256, 0, st>>>(A, T);
             for (int s = 0; s < max_pass; ++s)
                 k_tone_fft_pass<false><<<dim3(gx, ns, R), 256, 0, st>>>(A, T, s);
@@ -845,13 +852,14 @@ void launch_tone_batch(const VerifyArgs& A, void* items, int* n_items_dev, int n
             for (int s = 0; s < max_pass; ++s)
                 k_tone_fft_pass<true><<<dim3(gx, ns, R), 256, 0, st>>>(A, T, s);
             k_tone_stats<<<dim3(ns, R), 1024, 0, st>>>(A, T);
-            if (work_max > 0) {
+            }
+            if (work_max > 0 && T.frames && (parts & 2)) {
                 k_tone_frames<<<dim3((unsigned)((nf_max + kFramesPerCta - 1) / kFramesPerCta), ns, R), 256,
                                 (size_t)2 * wl * sizeof(double2) + (size_t)kFramesPerCta * wl * sizeof(double), st>>>(A, T);
                 k_tone_frame_stats<<<dim3((nf_max + 127) / 128, ns, R), 128, 0, st>>>(A, T);
             }
-            k_tone_final<<<(T.n_round * (int)ns + 3) / 4, 128, 0, st>>>(A, T, (int)ns);
-            *launches += 5 + 2 * max_pass + (work_max > 0 ? 2 : 0);
+            if (parts & 4) k_tone_final<<<(T.n_round * (int)ns + 3) / 4, 128, 0, st>>>(A, T, (int)ns);
+            *launches += 5 + 2 * max_pass + (work_max > 0 && T.frames ? 2 : 0);
             if (pass == 0 && !all_segments) {
                 k_tone_gate<<<(T.n_round + 63) / 64, 64, 0, st>>>(A, T, alive);
                 ++*launches;

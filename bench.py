@@ -357,6 +357,7 @@ def main() -> None:
     det.enable_profiling(True)
     det.stage_times_ms(reset=True)
     l0 = det.launch_count()
+    det.work_counters(reset=True)
     sampler = ClockSampler(local)
     sampler.start()
     ms_step, res = timed(resident, args.steps)
@@ -364,6 +365,7 @@ def main() -> None:
     sampler.join()
     launches = (det.launch_count() - l0) // args.steps
     stages = {k: v / args.steps for k, v in det.stage_times_ms(reset=True).items()}
+    phase2_work = {k: v // args.steps for k, v in det.work_counters(reset=True).items()}
     det.enable_profiling(False)
     through_host()                                       # untimed: first-use allocations of the host-input path
     ms_e2e, res_h = timed(through_host, args.steps)
@@ -430,6 +432,7 @@ def main() -> None:
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "stage_ms": stages,
+            "phase2_work_per_step": phase2_work,
         }
         line.update(extra)
         if shard_check is not None:

@@ -173,6 +173,9 @@ APD_API int apd_resample(const float* in_dev, int64_t n_in, int64_t in_stride, f
 
 /* Introspection for the bench: algorithmic byte counts and kernel launch counter. */
 APD_API int64_t apd_launch_count(apd_ctx* ctx);
+/* Phase-2 work since the last reset: out4 = {selected units (write-back inverse + find_peaks), candidate records,
+ * marker-tone work items, sub-batches}. */
+APD_API int apd_work_counters(apd_ctx* ctx, int64_t* out4, int reset);
 APD_API int apd_unit_n_out(apd_ctx* ctx, int32_t chunk, int32_t clip, int64_t total_samples, int32_t* n_out);
 
 #ifdef __cplusplus

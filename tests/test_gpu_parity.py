@@ -332,8 +332,9 @@ def test_sharded_archive_generator_is_world_size_independent():
 
 def test_tone_flank_gate_does_not_change_decisions():
     """Without a trace the flank transforms of tone candidates whose matched segment already fails are skipped
-    (verify.cu: k_tone_gate); the accept decisions, timestamps and the matched-segment metrics are those of the full
-    computation, and the flank metrics of the survivors are untouched."""
+    (verify.cu: k_tone_gate) and the flanks' frame metrics, which the decision never reads, are not computed; the accept
+    decisions, timestamps, the matched-segment metrics and the flank frequency / band purity of the survivors are
+    those of the full computation."""
     run = [r for r in FIXTURE_RUNS if r["wav"].endswith("radio1_2026-04-06_12_to_13_28m49_opening.wav") and r["sr"] == 8000][0]
     clips, audio = fixture_clips(run), fixture_audio(run)
     full = make_detector(clips, 8000, 60).scan_array(audio, collect_trace=True)
@@ -345,6 +346,7 @@ def test_tone_flank_gate_does_not_change_decisions():
     assert tone.any()
     assert np.array_equal(a["tone"][tone][:, 0, :], b["tone"][tone][:, 0, :])
     kept = tone & ((b["tone"][:, 1, :] != 0).any(axis=1) | (b["tone"][:, 2, :] != 0).any(axis=1))
-    assert np.array_equal(a["tone"][kept], b["tone"][kept])
+    assert np.array_equal(a["tone"][kept][:, :, :2], b["tone"][kept][:, :, :2])
+    assert not b["tone"][tone][:, 1:, 2:].any()
     accepted = tone & ((a["flags"] & 1) != 0)
     assert accepted.any() and not (accepted & ~kept).any()

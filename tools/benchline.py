@@ -9,4 +9,4 @@ st = d.get("stage_ms", {})
 print(tag, f"value={d['value']:.2f} h/s ms={d['ms_per_step']:.1f} e2e={d['e2e']['value']:.2f}",
       "stages:", {k: round(v, 1) for k, v in st.items()}, f"roofline={d['roofline']['frac']:.3f}",
       f"launches={d.get('gpu_launches')}", f"det={d['config'].get('detections_per_step')}",
-      f"clk={d.get('clocks', {}).get('sm_mhz')}")
+      f"clk={d.get('clocks', {}).get('sm_mhz')}", "p2:", d.get("phase2_work_per_step"))
