@@ -87,6 +87,15 @@ __device__ __forceinline__ UnitDesc load_desc(const UnitDesc* p)
     return d;
 }
 
+// A CTA whose units are all unused slots (phase 2 is launched for a full round of slots without waiting for the
+// selected count) leaves before it computes its twiddles.
+__device__ __forceinline__ bool any_unit_in_use(const UnitDesc* __restrict__ D, int u_begin, int u_end)
+{
+    bool any = false;
+    for (int u = u_begin; u < u_end; ++u) any |= __ldg(&D[u].n_out) >= 0;
+    return any;
+}
+
 constexpr int kN2 = 512;          // row length (complex)
 constexpr int kRowsPerCta = 4;    // 64 threads per row
 
@@ -128,6 +137,7 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
 {
     __shared__ __align__(1024) c2 buf[kRowsPerCta * 2 * kN2];
     const int tile = blockIdx.y, u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
+    if (!any_unit_in_use(D, u_begin, u_end)) return;
     const int q = threadIdx.x >> 6, j = threadIdx.x & 63;
     const int c = tile * kRowsPerCta + q;
     const RowAddr A(smem_addr(buf + q * (2 * kN2)), j);
@@ -252,6 +262,7 @@ k_corr_cols(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict
     c2* raw = reinterpret_cast<c2*>((reinterpret_cast<uintptr_t>(cols_smem) + AL - 1) & ~(AL - 1));
     const unsigned in0 = smem_addr(raw + 2 * N1 * kTB);
     const int tile = blockIdx.y, u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
+    if (!any_unit_in_use(D, u_begin, u_end)) return;
     const int p = threadIdx.x & 1, j = threadIdx.x >> 1;
     const bool act = 2 * T1 == ColThreads<S>::value || j < T1;  // N1 = 576: the last half warp only keeps the barriers
     const int bcol = tile * kTB + 2 * p;                     // first column of the pair
