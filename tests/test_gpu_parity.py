@@ -46,13 +46,22 @@ def test_batching_does_not_change_results():
     run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c10"][0]
     clips, audio = synthetic_inputs(run)
     ref = None
+    n_chunks = -(-len(audio) // (8000 * 10))
     for b in (1, 3, 16):
         det = make_detector(clips, 8000, 10, max_batch_chunks=b)
+        det.work_counters(reset=True)
         res = det.scan_array(audio)
         got = (res.peak_times, res.events)
         if ref is None:
             ref = got
         assert got == ref
+        # the phase-2 work counters bench.py reports: one record per candidate, one sub-batch per b chunks
+        work = det.work_counters()
+        assert work["candidate_records"] == len(res.records) == res.n_candidates
+        assert -(-n_chunks // b) <= work["sub_batches"] <= n_chunks      # host input is scanned in segments
+        assert 0 < work["selected_units"] <= n_chunks * len(clips)
+        assert work["tone_items"] == int(((res.records["flags"] >> 2) == 2).sum())
+        assert det.work_counters() == {k: 0 for k in work}
 
 
 def test_streaming_api_equals_array_scan():
