@@ -547,7 +547,9 @@ k_tone_stats(VerifyArgs A, ToneRound T)
 
 // STFT frame bins (du.py:77-100): a CTA owns kFramesPerCta consecutive frames of one (item, segment), stages their
 // windowed samples once in shared memory, then thread = (frame, bin) accumulates its DFT bin; |X|^2 into buffer B.
-constexpr int kFramesPerCta = 2;
+// For an even frame length the frame is folded first (one radix-2 step: even bins see x[n] + x[n + wl/2], odd bins
+// x[n] - x[n + wl/2]), which halves the multiply-adds of every bin.
+constexpr int kFramesPerCta = 8;
 
 __global__ void __launch_bounds__(256)
 k_tone_frames(VerifyArgs A, ToneRound T)
@@ -570,18 +572,31 @@ k_tone_frames(VerifyArgs A, ToneRound T)
         ftw[wl + t] = make_double2(wl > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(wl - 1)) : 1.0, 0.0);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < kFramesPerCta * wl; t += blockDim.x) {
-        const int fl = t / wl, n = t - fl * wl;
-        if (f0 + fl < nf) xw[t] = tone_sample(s, s.ms + (f0 + fl) * hop + n) * ftw[wl + n].x;
+    const bool fold = (wl & 1) == 0;
+    const int h = fold ? wl / 2 : wl;                                         // samples per bin after the fold
+    if (fold) {
+        for (int t = threadIdx.x; t < kFramesPerCta * h; t += blockDim.x) {
+            const int fl = t / h, n = t - fl * h;
+            if (f0 + fl >= nf) continue;
+            const int k0 = s.ms + (f0 + fl) * hop + n;
+            const double lo = tone_sample(s, k0) * ftw[wl + n].x, hi = tone_sample(s, k0 + h) * ftw[wl + n + h].x;
+            xw[fl * wl + n] = lo + hi;
+            xw[fl * wl + n + h] = lo - hi;
+        }
+    } else {
+        for (int t = threadIdx.x; t < kFramesPerCta * wl; t += blockDim.x) {
+            const int fl = t / wl, n = t - fl * wl;
+            if (f0 + fl < nf) xw[t] = tone_sample(s, s.ms + (f0 + fl) * hop + n) * ftw[wl + n].x;
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < kFramesPerCta * nbw; t += blockDim.x) {
         const int fl = t / nbw, kb = t - fl * nbw;
         if (f0 + fl >= nf) continue;
-        const double* __restrict__ x = xw + fl * wl;
+        const double* __restrict__ x = xw + fl * wl + ((fold && (kb & 1)) ? h : 0);
         double re = 0, im = 0;
         int ph = 0;
-        for (int n = 0; n < wl; ++n) {
+        for (int n = 0; n < h; ++n) {
             const double2 e = ftw[ph];
             re += x[n] * e.x;
             im += x[n] * e.y;
