@@ -212,7 +212,7 @@ class AudioPatternDetector:
             d.samples = a.ctypes.data_as(C.POINTER(C.c_float))
             d.length = a.size
             d.strategy = _lib.STRATEGY_NORMAL
-            d.tone_hz = 0.0
+            d.tone_hz = nan                                                # none: normal verifier (reference :605-625)
             for k in ("minimum_band_purity", "minimum_active_frame_ratio", "minimum_longest_active_run",
                       "minimum_active_frame_mean_purity", "maximum_min_flank_purity", "maximum_max_flank_purity"):
                 setattr(d, k, nan)

@@ -34,7 +34,7 @@ namespace {
 
 struct ClipHost {
     int L = 0, sw = 0, group = 0, strategy = 0, is_short = 0;
-    double tone_hz = 0.0, lufs = 0.0;
+    double tone_hz = 0.0, lufs = 0.0;     // tone_hz: NaN = the clip takes the normal verifier
     float self_max = 0.0f;
     float* d_raw = nullptr;
     float* d_norm = nullptr;
@@ -427,7 +427,7 @@ static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_sam
             return fail(APD_ERR_INVALID, "seconds_per_chunk is too small for clip " + std::to_string(p));
         }
         cl.strategy = descs[p].strategy;
-        cl.tone_hz = descs[p].strategy == APD_STRATEGY_MARKER_TONE ? descs[p].tone_hz : 0.0;
+        cl.tone_hz = descs[p].strategy == APD_STRATEGY_MARKER_TONE ? descs[p].tone_hz : nan("");   // NaN: no tone verifier
         cl.is_short = (2LL * cl.L < sample_rate) ? 1 : 0;             // L/sr < 0.5 (apd.py:628)
         auto it = sw_to_group.find(cl.sw);
         if (it == sw_to_group.end()) {
@@ -587,7 +587,7 @@ static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_sam
                                  descs[p].minimum_longest_active_run, descs[p].minimum_active_frame_mean_purity,
                                  descs[p].maximum_min_flank_purity, descs[p].maximum_max_flank_purity};
         for (int k = 0; k < 6; ++k) h_thr[p * 6 + k] = given[k] == given[k] ? given[k] : defaults[k];
-        if (cl.strategy == APD_STRATEGY_MARKER_TONE && cl.tone_hz > 0.0) {
+        if (cl.strategy == APD_STRATEGY_MARKER_TONE && cl.tone_hz == cl.tone_hz) {
             int P = 2;
             // chirp-z over the K = L/2 + 1 bins the metrics use (not all L): the circular convolution only has to
             // hold indices k - n in (-L, K), so P >= L + K - 1 suffices (half the 2L - 1 of a full Bluestein DFT
@@ -1294,7 +1294,7 @@ extern "C" int apd_verify_tone(apd_ctx* c, int32_t clip, const float* section_de
     cudaStream_t st = (cudaStream_t)stream;
     if (!c || clip < 0 || clip >= c->n_clips || !section_dev || n <= 0 || !metrics15_host || !accept)
         return fail(APD_ERR_INVALID, "verify_tone: bad arguments");
-    if (c->tone_ctas <= 0 || c->clips[clip].strategy != APD_STRATEGY_MARKER_TONE || !(c->clips[clip].tone_hz > 0.0))
+    if (c->tone_ctas <= 0 || c->clips[clip].strategy != APD_STRATEGY_MARKER_TONE || c->clips[clip].tone_hz != c->clips[clip].tone_hz)
         return fail(APD_ERR_INVALID, "verify_tone: not a marker-tone clip");
     if (n > c->C) return fail(APD_ERR_INVALID, "verify_tone: section longer than a chunk");
     use_set(c, 0);

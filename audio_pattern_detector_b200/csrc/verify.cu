@@ -59,7 +59,7 @@ k_verify_normal(VerifyArgs A, int nslots)
     for (int slot = blockIdx.y; slot < nslots && A.pk.slot0 + slot < nsel; slot += gridDim.y) {
     const int2 unit = A.pk.sel[A.pk.slot0 + slot];
     const int clip = unit.y;
-    if (A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0) continue;
+    if (A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] == A.cv.tone_hz[clip]) continue;   // not NaN
     long long start;
     int nsec;
     section_bounds(A.pk.geom[A.pk.clip_group[clip]], unit.x, start, nsec);
@@ -285,7 +285,7 @@ __global__ void k_tone_collect(VerifyArgs A, int nslots, ToneItem* items, int* n
     for (int s = 0; s < nslots; ++s) {
         if (A.pk.slot0 + s >= *A.pk.sel_count) break;
         const int2 u = A.pk.sel[A.pk.slot0 + s];
-        if (!(A.cv.strategy[u.y] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[u.y] > 0.0)) continue;
+        if (!(A.cv.strategy[u.y] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[u.y] == A.cv.tone_hz[u.y])) continue;
         for (int p = 0; p < A.pk.n_peaks[s]; ++p) {
             if (cnt < capacity)
                 items[cnt] = ToneItem{u.x, u.y, A.pk.peaks[(long long)s * A.pk.peak_stride + p],
@@ -760,7 +760,7 @@ __global__ void k_tone_decide(VerifyArgs A, const ToneItem* __restrict__ items, 
 __device__ __forceinline__ bool is_tone_slot(const VerifyArgs& A, int s)
 {
     const int clip = A.pk.sel[A.pk.slot0 + s].y;
-    return A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] > 0.0;
+    return A.cv.strategy[clip] == APD_STRATEGY_MARKER_TONE && A.cv.tone_hz[clip] == A.cv.tone_hz[clip];
 }
 
 // Ordered gather of the per-slot records (normal / short clips) into the output list: one thread per slot

@@ -67,7 +67,8 @@ typedef struct {
     const float* samples;         /* float32 mono at the detector sample rate (un-normalised, as loaded) */
     int32_t length;
     int32_t strategy;             /* APD_STRATEGY_* */
-    double tone_hz;               /* marker tone only: dominant frequency; <= 0 if unknown */
+    double tone_hz;               /* marker tone only: dominant frequency (any number, 0 Hz included, as apd.py:214-221);
+                                     NaN = none known: the clip takes the normal verifier (apd.py:605-625) */
     double minimum_band_purity;
     double minimum_active_frame_ratio;
     double minimum_longest_active_run;

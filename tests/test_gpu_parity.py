@@ -359,3 +359,23 @@ def test_tone_flank_gate_does_not_change_decisions():
     assert not b["tone"][tone][:, 1:, 2:].any()
     accepted = tone & ((a["flags"] & 1) != 0)
     assert accepted.any() and not (accepted & ~kept).any()
+
+
+def test_declared_zero_hz_is_a_tone_frequency_not_none():
+    """`dominant_frequency_hz = 0.0` is a number: the reference (:217-221, :605-620) sends such a clip's candidates to the
+    marker-tone verifier with f0 = 0 Hz (only `None` falls through to the normal verifier).  The C ABI says "none" with
+    NaN; 0 Hz must reach the device tone verifier and agree with the oracle."""
+    sr = 8000
+    rng = np.random.default_rng(3)
+    t = np.arange(int(0.6 * sr)) / sr
+    beep = (0.7 * np.sin(2 * np.pi * 950.0 * t)).astype(np.float32)
+    audio = (0.02 * rng.standard_normal(30 * sr)).astype(np.float32)
+    for at in (3.2, 9.9, 17.35):
+        audio[int(at * sr):int(at * sr) + beep.size] += beep
+    for f0 in (0.0, 950.0):
+        clips = [{"name": "beep", "audio": beep, "strategy": "marker_tone",
+                  "strategy_params": {"dominant_frequency_hz": f0}}]
+        out = compare_with_oracle(clips, audio, sr, 10, max_batch_chunks=2)
+        assert out["candidates"] >= 3 and out["tie_units"] == 0
+        assert all(c.kind == "tone" for c in out["result"].candidates)
+        assert out["accepted"] == (3 if f0 else 0)
