@@ -379,3 +379,21 @@ def test_declared_zero_hz_is_a_tone_frequency_not_none():
         assert out["candidates"] >= 3 and out["tie_units"] == 0
         assert all(c.kind == "tone" for c in out["result"].candidates)
         assert out["accepted"] == (3 if f0 else 0)
+
+
+def test_22050_hz_detector_matches_oracle():
+    """Any rate whose 100 ms gating hop is a whole number of samples is supported (here 2 205 = 21 cells of 105
+    samples); the generic four-step shapes serve its section sizes."""
+    sr = 22050
+    rng = np.random.default_rng(11)
+    t = np.arange(int(0.8 * sr)) / sr
+    chirp = (0.5 * np.sin(2 * np.pi * (400.0 + 900.0 * t) * t)).astype(np.float32)
+    jingle = (0.3 * rng.standard_normal(int(1.3 * sr))).astype(np.float32)
+    audio = (0.03 * rng.standard_normal(25 * sr)).astype(np.float32)
+    for at, clip in ((2.5, chirp), (9.7, jingle), (14.2, chirp), (19.6, jingle)):
+        audio[int(at * sr):int(at * sr) + clip.size] += clip
+    clips = [{"name": "chirp", "audio": chirp}, {"name": "jingle", "audio": jingle}]
+    out = compare_with_oracle(clips, audio, sr, 10, max_batch_chunks=2)
+    assert out["accepted"] == 4 and out["tie_units"] == 0
+    with pytest.raises(Exception, match="multiple of 10"):
+        make_detector([{"name": "chirp", "audio": chirp[:4000]}], 11025, 10)
