@@ -210,9 +210,9 @@ k_corr_rows(const UnitDesc* __restrict__ D, int nunits, int per, int M, float2* 
 // e^{+i pi m / N} / M with m = (j + 64 r) 512 + b factors into a per-thread scalar, folded into the last pass's
 // input twiddles, and per-output constants e^{i pi (r / (2 R2) + col / N)} kept in constant memory.
 constexpr int kTB = 4;
-__constant__ float2 c_post[3][2][10];        // [shape: 512, 576, 640][column of the pair][r]
+__constant__ float2 c_post[5][2][10];        // [shape: 384, 448, 512, 576, 640][column of the pair][r]
 
-template <class S> struct ShapeIndex { static constexpr int value = S::N == 512 ? 0 : (S::N == 576 ? 1 : 2); };
+template <class S> struct ShapeIndex { static constexpr int value = S::R2 - 6; };
 
 __device__ __forceinline__ void tma_load_tile3(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bytes,
                                                unsigned bar)
@@ -233,15 +233,20 @@ __device__ __forceinline__ float max_if_lt(float best, float y, int a, int b)
 // tmap: W seen as [8 * units][N1 / 8][512] 8-byte elements (row c = j + (N1 / 8) r is element (., j, r)); the box
 // {4, N1 / 8, 8} lands in shared memory as [c][4 columns].  NS = 1: the tile of the next unit is requested right after
 // the first exchange of the current one (the input buffer is free then), i.e. two passes ahead; NS = 2: a unit ahead.
-template <class S> struct ColThreads { static constexpr int value = (2 * (S::N / 8) + 31) / 32 * 32; };   // whole warps
+// two threads per butterfly; passes 1-2 have N1 / 8 butterflies per column, pass 3 always 64 (N1 = 384, 448: fewer
+// than 64 in passes 1-2; 576, 640: more)
+template <class S> struct ColThreads {
+    static constexpr int value = (2 * (S::N / 8 > 64 ? S::N / 8 : 64) + 31) / 32 * 32;                    // whole warps
+};
 
 // input tiles in flight per CTA: one (the next unit's tile is requested after the first exchange), which lets four
 // CTAs of N1 = 512 (3 x 16 KB) share an SM; two (a whole unit ahead) for N1 = 576, where a fourth CTA does not fit
 // but a fourth buffer does (measured equal to one)
 template <class S> struct ColStages { static constexpr int value = S::N == 576 ? 2 : 1; };
+template <class S, bool WRITE> struct ColCtas { static constexpr int value = WRITE ? 2 : (S::N <= 512 ? 4 : 3); };
 
 template <class S, bool WRITE, int NS>
-__global__ void __launch_bounds__(ColThreads<S>::value, WRITE ? 2 : (S::N == 512 ? 4 : 3))
+__global__ void __launch_bounds__(ColThreads<S>::value, ColCtas<S, WRITE>::value)
 k_corr_cols(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict__ D, int nunits, int per, int M,
             unsigned int* __restrict__ unit_max_bits, float* __restrict__ corr, long long corr_stride)
 {
@@ -264,7 +269,8 @@ k_corr_cols(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict
     const int tile = blockIdx.y, u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
     if (!any_unit_in_use(D, u_begin, u_end)) return;
     const int p = threadIdx.x & 1, j = threadIdx.x >> 1;
-    const bool act = 2 * T1 == ColThreads<S>::value || j < T1;  // N1 = 576: the last half warp only keeps the barriers
+    const bool act = 2 * T1 == ColThreads<S>::value || j < T1;  // threads past the butterflies of passes 1-2 keep the barriers
+    constexpr bool kAllLast = 2 * NLAST == ColThreads<S>::value;  // every thread owns a pass-3 butterfly
     const int bcol = tile * kTB + 2 * p;                     // first column of the pair
     const ColAddr<kTB> A(raw, j, 2 * p);
     const unsigned ld_in0 = in0 + 32u * (unsigned)j + 16u * (unsigned)p;
@@ -333,7 +339,7 @@ k_corr_cols(const __grid_constant__ CUtensorMap tmap, const UnitDesc* __restrict
         }
         __syncthreads();
         float best = 0.0f;
-        if (N1 == 512 || j < NLAST) {
+        if (kAllLast || j < NLAST) {
             ColLoad2<kTB, 64, R2, kBufB>::run(A, va, vb);
 #pragma unroll
             for (int r = 0; r < R2; ++r) { va[r] = cmul(va[r], tw3[r]); vb[r] = cmul(vb[r], tw3[r]); }
@@ -394,7 +400,10 @@ static int env_int2(const char* name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-bool corr_inv_supported(const Fft4Plan& P) { return P.N2 == kN2 && (P.N1 == 512 || P.N1 == 576 || P.N1 == 640); }
+bool corr_inv_supported(const Fft4Plan& P)
+{
+    return P.N2 == kN2 && (P.N1 == 384 || P.N1 == 448 || P.N1 == 512 || P.N1 == 576 || P.N1 == 640);
+}
 
 size_t corr_inv_desc_bytes(int nunits) { return sizeof(UnitDesc) * (size_t)(nunits > 0 ? nunits : 1); }
 
@@ -432,10 +441,10 @@ static void upload_post_constants()
 {
     static bool uploaded = false;
     if (uploaded) return;
-    float2 h[3][2][10];
-    const int r2[3] = {8, 9, 10};
-    const double n[3] = {2.0 * 512 * 512, 2.0 * 576 * 512, 2.0 * 640 * 512};
-    for (int sh = 0; sh < 3; ++sh)
+    float2 h[5][2][10];
+    const int r2[5] = {6, 7, 8, 9, 10};
+    const double n[5] = {2.0 * 384 * 512, 2.0 * 448 * 512, 2.0 * 512 * 512, 2.0 * 576 * 512, 2.0 * 640 * 512};
+    for (int sh = 0; sh < 5; ++sh)
         for (int col = 0; col < 2; ++col)
             for (int r = 0; r < 10; ++r) {
                 const double a = M_PI * ((double)r / (2.0 * r2[sh]) + (double)col / n[sh]);
@@ -474,7 +483,13 @@ void launch_corr_inv(const Fft4Plan& P, const UnitCtx& C, const float2* spec, lo
     // unit groups fastest: the CTAs of a tile run together, so the tile's clip rows stay in L1/L2 across the launch
     const dim3 gr(ny, P.N1 / kRowsPerCta), gc(ny, kN2 / kTB);
     k_corr_rows<<<gr, kRowsPerCta * 64, 0, st>>>(D, nunits, per, P.M, scratch);
-    if (P.N1 == 512) {
+    if (P.N1 == 384) {
+        if (write) launch_cols<Shape384, true>(*map, D, nunits, per, P.M, out, gc, st);
+        else launch_cols<Shape384, false>(*map, D, nunits, per, P.M, out, gc, st);
+    } else if (P.N1 == 448) {
+        if (write) launch_cols<Shape448, true>(*map, D, nunits, per, P.M, out, gc, st);
+        else launch_cols<Shape448, false>(*map, D, nunits, per, P.M, out, gc, st);
+    } else if (P.N1 == 512) {
         if (write) launch_cols<Shape512, true>(*map, D, nunits, per, P.M, out, gc, st);
         else launch_cols<Shape512, false>(*map, D, nunits, per, P.M, out, gc, st);
     } else if (P.N1 == 576) {

@@ -251,8 +251,12 @@ k_fwd_rows_fast(Fft4Plan P, const float2* __restrict__ T, float2* __restrict__ s
 // Column kernel: S::N = N1 = 8 * 8 * R2, TB adjacent columns on the lanes, threads = TB * (N1 / 8).
 // Fused with the section load: loudness gain, clamp, NaN scrub (lib.rs:220-227, apd.py:489-490), packing
 // u[m] = x[m] - i x[m + M] and the pre-twiddle e^{-i pi m / N}.  Exchange addressing: ColAddr / ColLoad.
+// Threads: TB per butterfly; passes 1-2 have N1 / 8 butterflies per column, pass 3 always 64 (N1 = 384, 448: fewer than 64
+// in passes 1-2, the surplus threads only keep the barriers there).
+template <class S, int TB> struct FwdThreads { static constexpr int value = TB * (S::N / 8 > 64 ? S::N / 8 : 64); };
+
 template <class S, int TB>
-__global__ void __launch_bounds__(TB * (S::N / 8), TB * (S::N / 8) <= 320 ? 2 : 1)
+__global__ void __launch_bounds__(FwdThreads<S, TB>::value, FwdThreads<S, TB>::value <= 320 ? 2 : 1)
 k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restrict__ gains, int gain_stride,
                 float2* __restrict__ T, int ntr, int per)
 {
@@ -263,6 +267,7 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restric
     extern __shared__ __align__(1024) unsigned char fwd_cols_smem[];           // two exchange buffers (dynamic: > 48 KB for TB = 8)
     c2* raw = reinterpret_cast<c2*>(fwd_cols_smem);
     const int q = threadIdx.x % TB, j = threadIdx.x / TB;
+    const bool act = T1 >= 64 || j < T1;                     // owns a butterfly of passes 1-2
     const int bcol = blockIdx.x * TB + q;
     const int M = P.M;
     const ColAddr<TB> A(raw, j, q);
@@ -304,22 +309,26 @@ k_fwd_cols_fast(Fft4Plan P, SectionGeom G, FwdGroups FG, const double* __restric
             x1[r] = m + M < n ? x[r * T1 * kRowN + M] : 0.0f;
         }
     };
-    if ((int)(blockIdx.y * per) < t_end) fetch(blockIdx.y * per);
+    if (act && (int)(blockIdx.y * per) < t_end) fetch(blockIdx.y * per);
     for (int t = blockIdx.y * per; t < t_end; ++t) {
         c2 v[R2 > 8 ? R2 : 8];
+        if (act) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            v[r] = cmul(mk(normalize_sample(x0[r], gain), -normalize_sample(x1[r], gain)), pre[r]);
-        Dft2<8, -1>::run(v);
-        col_store1<TB>(A, v);
-        if (t + 1 < t_end) fetch(t + 1);
+            for (int r = 0; r < 8; ++r)
+                v[r] = cmul(mk(normalize_sample(x0[r], gain), -normalize_sample(x1[r], gain)), pre[r]);
+            Dft2<8, -1>::run(v);
+            col_store1<TB>(A, v);
+            if (t + 1 < t_end) fetch(t + 1);
+        }
         __syncthreads();
-        ColLoad<TB, T1, 8>::run(A, v);
-        bfly_tw<8>(v, tw2);
-        Dft2<8, -1>::run(v);
-        col_store2<TB, kBufB>(A, v);
+        if (act) {
+            ColLoad<TB, T1, 8>::run(A, v);
+            bfly_tw<8>(v, tw2);
+            Dft2<8, -1>::run(v);
+            col_store2<TB, kBufB>(A, v);
+        }
         __syncthreads();
-        if (N1 == 512 || j < NLAST) {
+        if (T1 <= 64 || j < NLAST) {
             ColLoad<TB, 64, R2, kBufB>::run(A, v);
             bfly_tw<R2>(v, tw3);
             Dft2<R2, -1>::run(v);
@@ -347,17 +356,25 @@ static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G
                                  cudaStream_t st)
 {
     dim3 gc(P.N2 / TB, ny);
+    const size_t sm384 = (size_t)(2 * 384 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
+    const size_t sm448 = (size_t)(2 * 448 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
     const size_t sm512 = (size_t)(2 * 512 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
     const size_t sm576 = (size_t)(2 * 576 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
     const size_t sm640 = (size_t)(2 * 640 * TB + ColLayout<TB>::SLACK) * sizeof(c2);
     static bool attr = false;
     if (!attr) {
+        cudaFuncSetAttribute(k_fwd_cols_fast<Shape384, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm384);
+        cudaFuncSetAttribute(k_fwd_cols_fast<Shape448, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm448);
         cudaFuncSetAttribute(k_fwd_cols_fast<Shape512, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm512);
         cudaFuncSetAttribute(k_fwd_cols_fast<Shape576, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm576);
         cudaFuncSetAttribute(k_fwd_cols_fast<Shape640, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm640);
         attr = true;
     }
-    if (fs == 512)
+    if (fs == 384)
+        k_fwd_cols_fast<Shape384, TB><<<gc, TB * 64, sm384, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
+    else if (fs == 448)
+        k_fwd_cols_fast<Shape448, TB><<<gc, TB * 64, sm448, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
+    else if (fs == 512)
         k_fwd_cols_fast<Shape512, TB><<<gc, TB * 64, sm512, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
     else if (fs == 576)
         k_fwd_cols_fast<Shape576, TB><<<gc, TB * 72, sm576, st>>>(P, G, FG, gains, gain_stride, scratch, ntr, per);
@@ -368,6 +385,8 @@ static void launch_fwd_cols_fast(int fs, const Fft4Plan& P, const SectionGeom& G
 static int fast_shape(const Fft4Plan& P)
 {
     if (P.N2 != kRowN) return 0;
+    if (P.N1 == 384) return 384;
+    if (P.N1 == 448) return 448;
     if (P.N1 == 512) return 512;
     if (P.N1 == 576) return 576;
     if (P.N1 == 640) return 640;
@@ -423,15 +442,18 @@ bool build_plan(int M_min, Fft4Plan* plan, std::string* err)
                 for (int i = 0; i < c; ++i) v *= 5;
                 if (v <= 2048) n1s.push_back((int)v);
             }
+    n1s.push_back(448);                                      // 8 * 8 * 7: hot-shape kernels only (paired with 512 rows)
     double best_cost = 1e300;
     int bN1 = 0, bN2 = 0;
     for (int n2 = 32; n2 <= 1024; n2 *= 2)
         for (int n1 : n1s) {
             const long long M = (long long)n1 * n2;
             if (M < M_min) continue;
+            if (n1 == 448 && n2 != kRowN) continue;
             const double skew = std::fabs(std::log2((double)n1 / (double)n2));
             double cost = (double)M * (1.0 + 0.03 * skew);
-            if (n2 == kRowN && (n1 == 512 || n1 == 576 || n1 == 640)) cost *= 0.6;      // register-resident fast kernels exist
+            if (n2 == kRowN && (n1 == 384 || n1 == 448 || n1 == 512 || n1 == 576 || n1 == 640))
+                cost *= 0.6;                                                            // register-resident fast kernels exist
             if (cost < best_cost) { best_cost = cost; bN1 = n1; bN2 = n2; }
         }
     if (!bN1) {
@@ -440,7 +462,8 @@ bool build_plan(int M_min, Fft4Plan* plan, std::string* err)
     }
     Fft4Plan P;
     P.N1 = bN1; P.N2 = bN2; P.M = bN1 * bN2;
-    if (!factor(P.N1, &P.col) || !factor(P.N2, &P.row)) {
+    // (the generic kernels have no radix-7 pass; a 448 x 512 plan is only ever run by the hot-shape kernels)
+    if (!(factor(P.N1, &P.col) || fast_shape(P)) || !factor(P.N2, &P.row)) {
         if (err) *err = "internal: cannot factor sub-FFT length";
         return false;
     }

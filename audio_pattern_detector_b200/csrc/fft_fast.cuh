@@ -93,6 +93,45 @@ template <int SIGN> struct Dft2<3, SIGN> {
     }
 };
 
+// 6 = 2 x 3: DFT3 of the even and of the odd inputs, then w6^k o[k] = (cos(pi k / 3) + SIGN i sin(pi k / 3)) o[k]
+template <int SIGN> struct Dft2<6, SIGN> {
+    static __device__ __forceinline__ void run(c2* v)
+    {
+        const float s3 = 0.86602540378443864676f;           // sin(pi/3)
+        c2 e[3] = {v[0], v[2], v[4]};
+        c2 o[3] = {v[1], v[3], v[5]};
+        Dft2<3, SIGN>::run(e);
+        Dft2<3, SIGN>::run(o);
+        const c2 t1 = cmul(o[1], 0.5f, SIGN * s3), t2 = cmul(o[2], -0.5f, SIGN * s3);
+        v[0] = e[0] + o[0]; v[3] = e[0] - o[0];
+        v[1] = e[1] + t1;   v[4] = e[1] - t1;
+        v[2] = e[2] + t2;   v[5] = e[2] - t2;
+    }
+};
+
+// 7: a_k = v[k] + v[7-k], b_k = v[k] - v[7-k]; X[m], X[7-m] = (v0 + sum_k cos(2 pi k m / 7) a_k) +- SIGN i sum_k sin(2 pi k m / 7) b_k
+template <int SIGN> struct Dft2<7, SIGN> {
+    static __device__ __forceinline__ void run(c2* v)
+    {
+        const float c1 = 0.62348980185873353053f, c2_ = -0.22252093395631440429f, c3 = -0.90096886790241912624f;
+        const float s1 = 0.78183148246802980871f, s2 = 0.97492791218182360702f, s3 = 0.43388373911755812048f;
+        const c2 a1 = v[1] + v[6], b1 = v[1] - v[6];
+        const c2 a2 = v[2] + v[5], b2 = v[2] - v[5];
+        const c2 a3 = v[3] + v[4], b3 = v[3] - v[4];
+        const c2 x0 = v[0];
+        v[0] = x0 + a1 + a2 + a3;
+        const c2 p1 = axpy(axpy(axpy(x0, c1, a1), c2_, a2), c3, a3);
+        const c2 p2 = axpy(axpy(axpy(x0, c2_, a1), c3, a2), c1, a3);
+        const c2 p3 = axpy(axpy(axpy(x0, c3, a1), c1, a2), c2_, a3);
+        const c2 q1 = rot<SIGN>(axpy(axpy(mul2(b1, mk(s1, s1)), s2, b2), s3, b3));
+        const c2 q2 = rot<SIGN>(axpy(axpy(mul2(b1, mk(s2, s2)), -s3, b2), -s1, b3));
+        const c2 q3 = rot<SIGN>(axpy(axpy(mul2(b1, mk(s3, s3)), -s1, b2), s2, b3));
+        v[1] = p1 + q1; v[6] = p1 - q1;
+        v[2] = p2 + q2; v[5] = p2 - q2;
+        v[3] = p3 + q3; v[4] = p3 - q3;
+    }
+};
+
 // 9 = 3 x 3: DFT3 over r1 of v[3 r1 + r2], twiddles w9^{q1 r2}, DFT3 over r2 -> X[q1 + 3 q2]
 template <int SIGN> struct Dft2<9, SIGN> {
     static __device__ __forceinline__ void run(c2* v)
@@ -144,6 +183,8 @@ template <int N_, int R0_, int R1_, int R2_> struct Shape3 {
     static constexpr int N = N_, R0 = R0_, R1 = R1_, R2 = R2_;
     static_assert(R0_ * R1_ * R2_ == N_, "radices must multiply to N");
 };
+using Shape384 = Shape3<384, 8, 8, 6>;
+using Shape448 = Shape3<448, 8, 8, 7>;
 using Shape512 = Shape3<512, 8, 8, 8>;
 using Shape576 = Shape3<576, 8, 8, 9>;
 using Shape640 = Shape3<640, 8, 8, 10>;
@@ -311,7 +352,9 @@ template <int TB, int T, int R, int OFF = 0> struct ColLoad {
     static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* v)
     {
         v[0] = one<0>(A); v[1] = one<1>(A); v[2] = one<2>(A); v[3] = one<3>(A);
-        v[4] = one<4>(A); v[5] = one<5>(A); v[6] = one<6>(A); v[7] = one<7>(A);
+        v[4] = one<4>(A); v[5] = one<5>(A);
+        if (R >= 7) v[6] = one<6>(A);
+        if (R >= 8) v[7] = one<7>(A);
         if (R >= 9) v[8] = one<8>(A);
         if (R >= 10) v[9] = one<9>(A);
     }
@@ -334,7 +377,9 @@ template <int TB, int T, int R, int OFF = 0> struct ColLoad2 {
     static __device__ __forceinline__ void run(const ColAddr<TB>& A, c2* va, c2* vb)
     {
         one<0>(A, va, vb); one<1>(A, va, vb); one<2>(A, va, vb); one<3>(A, va, vb);
-        one<4>(A, va, vb); one<5>(A, va, vb); one<6>(A, va, vb); one<7>(A, va, vb);
+        one<4>(A, va, vb); one<5>(A, va, vb);
+        if (R >= 7) one<6>(A, va, vb);
+        if (R >= 8) one<7>(A, va, vb);
         if (R >= 9) one<8>(A, va, vb);
         if (R >= 10) one<9>(A, va, vb);
     }

@@ -441,7 +441,7 @@ def main() -> None:
             achieved = alg_bytes / 1e9 / (iso_ms / 1000.0)
             achieved_in_step = alg_bytes / 1e9 / (stages["correlate_max"] / 1000.0)
             # DRAM traffic of the pair per step, from the ncu capture of the 640 x 512 shape scaled by M per shape class
-            m_of = lambda no: 512 * (512 if no <= 524288 else (576 if no <= 589824 else 640))        # noqa: E731
+            m_of = lambda no: 512 * next(n1 for n1 in (384, 448, 512, 576, 640) if no <= 1024 * n1 or n1 == 640)        # noqa: E731
             traffic = sum(TRAFFIC_BYTES_PER_UNIT_640 * m_of(int(C_ + s + L - 1)) / (640 * 512)
                           for s, L in zip(sw_arr, L_arr)) * len(my_chunks)
             line["roofline"] = {

@@ -397,3 +397,25 @@ def test_22050_hz_detector_matches_oracle():
     assert out["accepted"] == 4 and out["tie_units"] == 0
     with pytest.raises(Exception, match="multiple of 10"):
         make_detector([{"name": "chirp", "audio": chirp[:4000]}], 11025, 10)
+
+
+def test_hot_shapes_384_and_448():
+    """40 s chunks at 8 kHz put N_out at 330-390 k (N1 = 384 = 8 x 8 x 6) and 410-450 k (N1 = 448 = 8 x 8 x 7): the
+    radix-6 / radix-7 last passes of the hot-shape kernels, forward and inverse, both phases."""
+    sr = 8000
+    rng = np.random.default_rng(21)
+    t1 = np.arange(int(1.2 * sr)) / sr
+    short = (0.5 * np.sin(2 * np.pi * (300.0 + 700.0 * t1) * t1)).astype(np.float32)          # sw 2 s: N_out 345 599
+    long_ = (0.3 * rng.standard_normal(int(6.3 * sr))).astype(np.float32)                    # sw 7 s: N_out 426 399
+    tone = (0.6 * np.sin(2 * np.pi * 1040.0 * np.arange(int(2.5 * sr)) / sr)).astype(np.float32)   # sw 3 s: 363 999
+    audio = (0.03 * rng.standard_normal(130 * sr)).astype(np.float32)
+    for at, clip in ((5.0, short), (39.7, long_), (61.3, tone), (79.9, short), (100.2, long_), (121.0, tone)):
+        audio[int(at * sr):int(at * sr) + clip.size] += clip
+    clips = [{"name": "short", "audio": short}, {"name": "long", "audio": long_},
+             {"name": "tone", "audio": tone, "strategy": "marker_tone",
+              "strategy_params": {"dominant_frequency_hz": 1040.0}}]
+    det = make_detector(clips, sr, 40)
+    assert [det.clip_info(i)["fft_points"] for i in range(3)] == [2 * 384 * 512, 2 * 448 * 512, 2 * 384 * 512]
+    out = compare_with_oracle(clips, audio, sr, 40, max_batch_chunks=3)
+    assert out["accepted"] == 6 and out["tie_units"] == 0
+    assert out["worst_absmax_rel"] < 1e-5
