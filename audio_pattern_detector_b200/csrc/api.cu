@@ -654,6 +654,7 @@ static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_sam
     long long max_sec = c->C;
     for (auto& g : c->groups) max_sec = std::max(max_sec, c->C + g.halo);
     c->cells_stride = (int)((max_sec + c->kw.cell - 1) / c->kw.cell + 1);
+    if (c->kw.general) c->cells_stride = (int)(G * ((max_sec + c->kw.cell - 1) / c->kw.cell + 4));   // block slots per group
     CK(dalloc(&c->d_kw_state, (size_t)B * c->cells_stride * 4));
     CK(dalloc(&c->d_kw_energy, (size_t)B * c->cells_stride));
     CK(dalloc(&c->d_kw_em1, (size_t)B));

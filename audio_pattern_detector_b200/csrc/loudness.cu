@@ -21,8 +21,9 @@
 // those first cells are re-filtered from zero state (k_kw_patch) and every later cell energy is, to
 // float64 rounding, the union's.
 //
-// Restriction: the gating hop 0.1*sr must be an integer number of samples
-// (sr % 10 == 0) so that block edges fall on cell edges; apd_create rejects other rates.
+// The cell scheme needs the gating hop 0.1*sr to be a whole number of samples (sr % 10 == 0) so that block edges
+// fall on cell edges; other rates take the serial general-rate kernel at the end of this file (k_kw_serial).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -364,6 +365,82 @@ __global__ void k_kw_gate(KwConfig K, SectionGeom Gu, const SectionGeom* __restr
     }
 }
 
+// General-rate path (0.1 * sample_rate is not a whole number of samples, e.g. 11 025 Hz): the block bounds of
+// lib.rs:113-122 then fall on no cell grid, so the section is filtered the way the reference writes it - one serial
+// float64 recurrence per (chunk, group), one thread each - with the squared prefix sampled at the truncated block
+// bounds as the thread passes them.  Slow (a thread walks its whole section) but exact; the cell-parallel kernels
+// above serve every rate that is a multiple of 10 Hz.  ms[(ci * G + g) * ms_stride + j]: mean square of block j.
+__global__ void k_kw_serial(KwConfig K, const SectionGeom* __restrict__ geoms, int nsec, int G, long long ms_stride,
+                            double* __restrict__ ms_all, double* __restrict__ lufs_out, double* __restrict__ gain_out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsec * G) return;
+    const int ci = t / G, g = t % G;
+    long long start;
+    int n;
+    section_bounds(geoms[g], ci, start, n);
+    const double NEG_INF = -INFINITY;
+    double lufs = NEG_INF;
+    if (n > 0) {
+        const float* __restrict__ x = geoms[g].audio + (start - geoms[g].base);
+        double* __restrict__ ms = ms_all + (long long)t * ms_stride;
+        const double rate = (double)K.rate;
+        const double T = __ddiv_rn((double)n, rate);
+        const double block = T < 0.5 ? T : 0.4;                                   // apd.py:417
+        const double win = __dmul_rn(block, rate), hop = __dmul_rn(win, 0.25);    // lib.rs:142-146
+        long long nb = llround(__ddiv_rn(__dsub_rn(T, block), __dmul_rn(block, 0.25))) + 1;   // lib.rs:149
+        if (nb > ms_stride) nb = ms_stride;                                       // (sized for the longest section)
+        auto lo_of = [&](long long j) { return (long long)__dmul_rn((double)j, hop); };
+        auto hi_of = [&](long long j) {
+            const long long h = (long long)__dadd_rn(__dmul_rn((double)j, hop), win);
+            return h > n ? (long long)n : h;
+        };
+        double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v, P = 0;
+        long long jl = 0, jh = 0;                            // next block whose lower / upper bound is still ahead
+        long long next_lo = nb > 0 ? lo_of(0) : -1, next_hi = nb > 0 ? hi_of(0) : -1;
+        for (int p = 0; p <= n; ++p) {                       // P = sum of the first p squared K-weighted samples
+            while (jl < nb && next_lo == p) {
+                ms[jl] = P;                                  // prefix at the lower bound, replaced by the mean square below
+                ++jl;
+                next_lo = jl < nb ? lo_of(jl) : -1;
+            }
+            while (jh < nb && next_hi == p) {
+                const long long lo = lo_of(jh);
+                ms[jh] = lo < p ? (P - ms[jh]) / (double)(p - lo) : -1.0;       // lib.rs:119 (lo >= hi: skipped)
+                ++jh;
+                next_hi = jh < nb ? hi_of(jh) : -1;
+            }
+            if (p < n) {
+                kw_step(K.cf, (double)x[p], s1, s2, h1, h2, v);
+                P += v * v;
+            }
+        }
+        for (long long j = jl > jh ? jh : jl; j < nb; ++j) ms[j] = -1.0;          // bounds at or past the end: lo >= hi
+        if (nb <= 0) {
+            const double m = P / (double)n;
+            lufs = m <= 0.0 ? NEG_INF : -0.691 + 10.0 * log10(m);
+        } else {
+            double gate = NEG_INF;
+            for (int pass = 0; pass < 2; ++pass) {
+                double sum = 0, cnt = 0;
+                for (long long j = 0; j < nb; ++j) {
+                    const double m = ms[j];
+                    if (m <= 0.0) continue;
+                    const double l = -0.691 + 10.0 * log10(m);
+                    const bool keep = pass == 0 ? (l >= -70.0) : (l > gate && l >= -70.0);
+                    if (keep) { sum += m; cnt += 1.0; }
+                }
+                if (cnt == 0.0) { lufs = NEG_INF; break; }
+                const double mean = sum / cnt;
+                if (pass == 0) gate = -0.691 + 10.0 * log10(mean) - 10.0;
+                else lufs = -0.691 + 10.0 * log10(mean);
+            }
+        }
+    }
+    lufs_out[t] = lufs;
+    gain_out[t] = pow(10.0, (kTargetLufs - lufs) / 20.0);   // lib.rs:221-222
+}
+
 // ------------------------------------------------------------------ host side
 static void kw_coefficients(double rate, double cf[12])          // lib.rs:13-53
 {
@@ -393,14 +470,24 @@ static void kw_coefficients(double rate, double cf[12])          // lib.rs:13-53
 
 bool kw_config_create(int sample_rate, KwConfig* out, std::string* err)
 {
-    if (sample_rate <= 0 || sample_rate % 10 != 0) {
-        if (err) *err = "sample rate must be a positive multiple of 10 Hz (100 ms gating hop must be whole samples)";
+    if (sample_rate <= 0) {
+        if (err) *err = "sample rate must be positive";
         return false;
     }
     KwConfig K;
     memset(&K, 0, sizeof(K));
     K.rate = sample_rate;
     kw_coefficients((double)sample_rate, K.cf);
+    if (sample_rate % 10 != 0) {
+        // the 100 ms gating hop is not a whole number of samples: serial general-rate path (k_kw_serial); `cell` only
+        // sizes the workspace then (at least one slot per gating block)
+        K.general = 1;
+        K.cell = std::max(1, sample_rate / 10);
+        K.k_per_hop = 1;
+        K.patch_cells = 1;
+        *out = K;
+        return true;
+    }
     const int hop = sample_rate / 10;
     int k = 1;
     while (k <= hop && !(hop % k == 0 && hop / k <= 128)) ++k;
@@ -484,6 +571,11 @@ void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom
                      double* energy_m1, double* patch, double* lufs, double* gain, cudaStream_t st)
 {
     if (nsec <= 0) return;
+    if (K.general) {
+        // energy[] is the per-(chunk, group) block workspace: cells_stride / G slots each
+        k_kw_serial<<<(nsec * G + 31) / 32, 32, 0, st>>>(K, d_geoms, nsec, G, (long long)(cells_stride / G), energy, lufs, gain);
+        return;
+    }
     static bool attr = false;
     const size_t smem = (size_t)128 * (K.cell + 1) * sizeof(float);
     if (!attr) {

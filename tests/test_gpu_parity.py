@@ -395,8 +395,27 @@ def test_22050_hz_detector_matches_oracle():
     clips = [{"name": "chirp", "audio": chirp}, {"name": "jingle", "audio": jingle}]
     out = compare_with_oracle(clips, audio, sr, 10, max_batch_chunks=2)
     assert out["accepted"] == 4 and out["tie_units"] == 0
-    with pytest.raises(Exception, match="multiple of 10"):
-        make_detector([{"name": "chirp", "audio": chirp[:4000]}], 11025, 10)
+
+
+def test_11025_hz_general_rate_loudness_matches_oracle():
+    """0.1 * 11 025 is not a whole number of samples: the gating blocks' truncated bounds (lib.rs:113-122) fall on no
+    cell grid, and the loudness takes the serial general-rate kernel (k_kw_serial) - same LUFS, gains and detections as
+    the oracle, short (< 0.5 s, single-block) clip included."""
+    sr = 11025
+    rng = np.random.default_rng(12)
+    t = np.arange(int(0.9 * sr)) / sr
+    chirp = (0.5 * np.sin(2 * np.pi * (300.0 + 800.0 * t) * t)).astype(np.float32)
+    blip = (0.4 * rng.standard_normal(int(0.31 * sr))).astype(np.float32)
+    audio = (0.03 * rng.standard_normal(int(34.7 * sr))).astype(np.float32)
+    audio[5 * sr:6 * sr] = 0.0                                                    # a silent second inside a chunk
+    for at, clip in ((2.5, chirp), (9.8, blip), (14.2, chirp), (19.9, blip), (27.3, chirp)):
+        audio[int(at * sr):int(at * sr) + clip.size] += clip
+    clips = [{"name": "chirp", "audio": chirp}, {"name": "blip", "audio": blip}]
+    out = compare_with_oracle(clips, audio, sr, 10, max_batch_chunks=2)
+    assert out["accepted"] == 5 and out["tie_units"] == 0
+    silent = np.zeros(12 * sr, dtype=np.float32)
+    quiet = compare_with_oracle(clips, silent, sr, 10)
+    assert quiet["candidates"] == 0
 
 
 def test_hot_shapes_384_and_448():
