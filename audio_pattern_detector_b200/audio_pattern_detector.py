@@ -115,6 +115,10 @@ class ScanResult:
         return int(self.records.shape[0])
 
     @property
+    def clip_names(self) -> list[str]:
+        return list(self._clip_names)
+
+    @property
     def candidates(self) -> list[Candidate]:
         if self._candidates is None:
             out = []

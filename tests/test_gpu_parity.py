@@ -438,3 +438,19 @@ def test_hot_shapes_384_and_448():
     out = compare_with_oracle(clips, audio, sr, 40, max_batch_chunks=3)
     assert out["accepted"] == 6 and out["tie_units"] == 0
     assert out["worst_absmax_rel"] < 1e-5
+
+
+def test_pattern_split_equals_full_scan():
+    """Splitting the PATTERN list instead of the chunk range (the alternative partition of SURVEY.md section 8e, for
+    short streams against many patterns): two detectors, each over all chunks and half of the clips, merged by
+    sharding.merge_pattern_shards, give the single detector's peak times and callback order."""
+    from audio_pattern_detector_b200 import sharding
+    run = [r for r in SYN_RUNS if r["case"]["id"] == "s8k_c10"][0]
+    clips, audio = synthetic_inputs(run)
+    full = make_detector(clips, 8000, 10).scan_array(audio)
+    assert len(clips) >= 2 and len(full.events) > 0
+    k = len(clips) // 2
+    shards = [sharding.detections_of(make_detector(part, 8000, 10).scan_array(audio), off)
+              for part, off in ((clips[:k], 0), (clips[k:], k))]
+    times, events = sharding.merge_pattern_shards(shards, [c["name"] for c in clips])
+    assert times == full.peak_times and events == full.events

@@ -88,3 +88,64 @@ def test_two_rank_gloo_scan_equals_single_process():
     want = scan(0, n_chunks)
     assert n_chunks >= 4 and sum(len(v) for v in want[0].values()) > 0
     assert got[0] == want[0] and got[1] == want[1]
+
+
+# ---- the other axis: every rank scans all chunks against a slice of the pattern list ----
+def _oracle_pattern_scanner(pats, audio, sr, spc):
+    from oracle.detector import OracleDetector
+
+    def scan(p0, p1):
+        det = OracleDetector(pats[p0:p1], sr, spc, precision="f32")
+        _, events, _ = det.run(audio)
+        index = {p["name"]: p0 + k for k, p in enumerate(pats[p0:p1])}
+        return [(chunk, t, index[name], name) for t, name, chunk, _ in events]
+    return scan
+
+
+def test_pattern_ranges_and_merge_order():
+    assert [sharding.pattern_range_for_rank(5, 3, r) for r in range(3)] == [(0, 2), (2, 4), (4, 5)]
+    names = ["a", "b", "c"]
+    shard0 = [(0, 2.0, 0, "a"), (1, 5.0, 0, "a"), (1, 5.5, 1, "b")]
+    shard1 = [(0, 1.0, 2, "c"), (1, 5.0, 2, "c"), (1, 4.0, 2, "c")]
+    times, events = sharding.merge_pattern_shards([shard0, shard1], names)
+    # chunk by chunk, by timestamp, equal timestamps in clip-list order
+    assert events == [(1.0, "c"), (2.0, "a"), (4.0, "c"), (5.0, "a"), (5.0, "c"), (5.5, "b")]
+    assert times == {"a": [2.0, 5.0], "b": [5.5], "c": [1.0, 4.0, 5.0]}
+    assert sharding.merge_pattern_shards([], names) == ({"a": [], "b": [], "c": []}, [])
+
+
+def _pattern_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sr, spc, pats, audio = _inputs()
+        out = sharding.sharded_scan_by_pattern(_oracle_pattern_scanner(pats, audio, sr, spc), [p["name"] for p in pats])
+        if rank == 0:
+            q.put(out)
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_pattern_split_equals_single_process():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pattern_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sr, spc, pats, audio = _inputs()
+    scan, n_chunks = _oracle_scanner(pats, audio, sr, spc)
+    want = scan(0, n_chunks)
+    assert sum(len(v) for v in want[0].values()) > 0
+    assert got[0] == want[0] and got[1] == want[1]
