@@ -398,21 +398,42 @@ __global__ void k_kw_serial(KwConfig K, const SectionGeom* __restrict__ geoms, i
         double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v, P = 0;
         long long jl = 0, jh = 0;                            // next block whose lower / upper bound is still ahead
         long long next_lo = nb > 0 ? lo_of(0) : -1, next_hi = nb > 0 ? hi_of(0) : -1;
-        for (int p = 0; p <= n; ++p) {                       // P = sum of the first p squared K-weighted samples
-            while (jl < nb && next_lo == p) {
-                ms[jl] = P;                                  // prefix at the lower bound, replaced by the mean square below
-                ++jl;
-                next_lo = jl < nb ? lo_of(jl) : -1;
-            }
-            while (jh < nb && next_hi == p) {
-                const long long lo = lo_of(jh);
-                ms[jh] = lo < p ? (P - ms[jh]) / (double)(p - lo) : -1.0;       // lib.rs:119 (lo >= hi: skipped)
-                ++jh;
-                next_hi = jh < nb ? hi_of(jh) : -1;
-            }
-            if (p < n) {
-                kw_step(K.cf, (double)x[p], s1, s2, h1, h2, v);
-                P += v * v;
+        // P = sum of the first p squared K-weighted samples; block bounds are handled as the walk reaches them.
+        // Samples are fetched 32 at a time so that the loads of a tile are in flight together (one load per step left
+        // the thread waiting a full memory latency per sample).
+        auto next_event = [&]() {
+            long long e = (long long)n + 1;
+            if (jl < nb && next_lo < e) e = next_lo;
+            if (jh < nb && next_hi < e) e = next_hi;
+            return e;
+        };
+        long long evt = next_event();
+        for (int p0 = 0; p0 <= n; p0 += 32) {
+            float xs[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) xs[k] = p0 + k < n ? x[p0 + k] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int p = p0 + k;
+                if (p > n) break;
+                if (p == evt) {
+                    while (jl < nb && next_lo == p) {
+                        ms[jl] = P;                          // prefix at the lower bound, replaced by the mean square below
+                        ++jl;
+                        next_lo = jl < nb ? lo_of(jl) : -1;
+                    }
+                    while (jh < nb && next_hi == p) {
+                        const long long lo = lo_of(jh);
+                        ms[jh] = lo < p ? (P - ms[jh]) / (double)(p - lo) : -1.0;   // lib.rs:119 (lo >= hi: skipped)
+                        ++jh;
+                        next_hi = jh < nb ? hi_of(jh) : -1;
+                    }
+                    evt = next_event();
+                }
+                if (p < n) {
+                    kw_step(K.cf, (double)xs[k], s1, s2, h1, h2, v);
+                    P += v * v;
+                }
             }
         }
         for (long long j = jl > jh ? jh : jl; j < nb; ++j) ms[j] = -1.0;          // bounds at or past the end: lo >= hi
