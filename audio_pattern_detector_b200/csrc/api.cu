@@ -506,7 +506,7 @@ static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_sam
     CK(dalloc(&d_tpatch, (size_t)c->kw.patch_cells));
     int max_L = 0;
     for (auto& cl : c->clips) max_L = std::max(max_L, cl.L);
-    const int clip_cells = (max_L + c->kw.cell - 1) / c->kw.cell + 1;
+    const int clip_cells = (c->kw.general ? 2 : 1) * ((max_L + c->kw.cell - 1) / c->kw.cell + 4);
     CK(dalloc(&d_tstate, (size_t)clip_cells * 4));
     CK(dalloc(&d_ten, (size_t)clip_cells));
     CK(dalloc(&d_tem1, 1));
@@ -654,7 +654,7 @@ static int create_ctx(apd_ctx* c, int device, int sample_rate, int64_t chunk_sam
     long long max_sec = c->C;
     for (auto& g : c->groups) max_sec = std::max(max_sec, c->C + g.halo);
     c->cells_stride = (int)((max_sec + c->kw.cell - 1) / c->kw.cell + 1);
-    if (c->kw.general) c->cells_stride = (int)(G * ((max_sec + c->kw.cell - 1) / c->kw.cell + 4));   // block slots per group
+    if (c->kw.general) c->cells_stride = (int)(G * 2 * ((max_sec + c->kw.cell - 1) / c->kw.cell + 4));   // 2 block slots per group
     CK(dalloc(&c->d_kw_state, (size_t)B * c->cells_stride * 4));
     CK(dalloc(&c->d_kw_energy, (size_t)B * c->cells_stride));
     CK(dalloc(&c->d_kw_em1, (size_t)B));

@@ -366,14 +366,20 @@ __global__ void k_kw_gate(KwConfig K, SectionGeom Gu, const SectionGeom* __restr
 }
 
 // General-rate path (0.1 * sample_rate is not a whole number of samples, e.g. 11 025 Hz): the block bounds of
-// lib.rs:113-122 then fall on no cell grid, so the section is filtered the way the reference writes it - one serial
-// float64 recurrence per (chunk, group), one thread each - with the squared prefix sampled at the truncated block
-// bounds as the thread passes them.  Slow (a thread walks its whole section) but exact; the cell-parallel kernels
-// above serve every rate that is a multiple of 10 Hz.  ms[(ci * G + g) * ms_stride + j]: mean square of block j.
-__global__ void k_kw_serial(KwConfig K, const SectionGeom* __restrict__ geoms, int nsec, int G, long long ms_stride,
-                            double* __restrict__ ms_all, double* __restrict__ lufs_out, double* __restrict__ gain_out)
+// lib.rs:113-122 then fall on no cell grid.  One WARP per (chunk, group) section: the section is cut into 32 slices, lane
+// w filters its slice with the serial float64 recurrence after a warm-up of K.warm samples from zero state (the
+// K-weighting filters have forgotten their start state by then: n^2 r^n < 1e-20, the argument of k_kw_patch; a slice
+// that starts within K.warm samples of the section start simply starts there, exactly), accumulates the squared
+// prefix LOCAL to the slice and samples it at the truncated block bounds it passes.  A warp scan of the slice totals
+// turns the local prefixes into the reference's P[hi] - P[lo] (same sums, re-associated), then the two gates run
+// with the blocks spread over the lanes.  work[(ci * G + g) * stride ...]: [0, stride/2) prefix at lower bounds, then
+// mean squares; [stride/2, stride) prefix at upper bounds.
+__global__ void __launch_bounds__(128)
+k_kw_serial(KwConfig K, const SectionGeom* __restrict__ geoms, int nsec, int G, long long stride,
+            double* __restrict__ work_all, double* __restrict__ lufs_out, double* __restrict__ gain_out)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= nsec * G) return;
     const int ci = t / G, g = t % G;
     long long start;
@@ -381,76 +387,104 @@ __global__ void k_kw_serial(KwConfig K, const SectionGeom* __restrict__ geoms, i
     section_bounds(geoms[g], ci, start, n);
     const double NEG_INF = -INFINITY;
     double lufs = NEG_INF;
-    if (n > 0) {
+    if (n > 0) {                                             // warp-uniform
         const float* __restrict__ x = geoms[g].audio + (start - geoms[g].base);
-        double* __restrict__ ms = ms_all + (long long)t * ms_stride;
+        double* __restrict__ plo = work_all + (long long)t * stride;
+        double* __restrict__ phi = plo + stride / 2;
         const double rate = (double)K.rate;
         const double T = __ddiv_rn((double)n, rate);
         const double block = T < 0.5 ? T : 0.4;                                   // apd.py:417
         const double win = __dmul_rn(block, rate), hop = __dmul_rn(win, 0.25);    // lib.rs:142-146
         long long nb = llround(__ddiv_rn(__dsub_rn(T, block), __dmul_rn(block, 0.25))) + 1;   // lib.rs:149
-        if (nb > ms_stride) nb = ms_stride;                                       // (sized for the longest section)
+        if (nb > stride / 2) nb = stride / 2;                                     // (sized for the longest section)
         auto lo_of = [&](long long j) { return (long long)__dmul_rn((double)j, hop); };
         auto hi_of = [&](long long j) {
             const long long h = (long long)__dadd_rn(__dmul_rn((double)j, hop), win);
             return h > n ? (long long)n : h;
         };
-        double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v, P = 0;
-        long long jl = 0, jh = 0;                            // next block whose lower / upper bound is still ahead
-        long long next_lo = nb > 0 ? lo_of(0) : -1, next_hi = nb > 0 ? hi_of(0) : -1;
-        // P = sum of the first p squared K-weighted samples; block bounds are handled as the walk reaches them.
-        // Samples are fetched 32 at a time so that the loads of a tile are in flight together (one load per step left
-        // the thread waiting a full memory latency per sample).
-        auto next_event = [&]() {
-            long long e = (long long)n + 1;
-            if (jl < nb && next_lo < e) e = next_lo;
-            if (jh < nb && next_hi < e) e = next_hi;
-            return e;
-        };
-        long long evt = next_event();
-        for (int p0 = 0; p0 <= n; p0 += 32) {
-            float xs[32];
+        const int len = (n + 31) / 32;                       // slice length
+        const int last_lane = (n - 1) / len;                 // last non-empty slice
+        auto lane_of = [&](long long pos) { return pos >= n ? last_lane : (int)(pos / len); };
+        const int a = min(n, lane * len), b = min(n, a + len);
+        // this lane records the bounds at positions [a, b), and position n as well if it owns the section's end
+        const long long own_hi = (lane == last_lane) ? (long long)n + 1 : (long long)b;
+        double P = 0;
+        if (a < b) {
+            long long jl = 0, jh = 0;
+            while (jl < nb && lo_of(jl) < a) ++jl;
+            while (jh < nb && hi_of(jh) < a) ++jh;
+            long long next_lo = jl < nb ? lo_of(jl) : -1, next_hi = jh < nb ? hi_of(jh) : -1;
+            auto next_event = [&]() {
+                long long e = own_hi;
+                if (jl < nb && next_lo < e) e = next_lo;
+                if (jh < nb && next_hi < e) e = next_hi;
+                return e;
+            };
+            long long evt = next_event();
+            double s1 = 0, s2 = 0, h1 = 0, h2 = 0, v;
+            const int w0 = max(0, a - K.warm);
+            for (int p0 = w0; p0 <= b; p0 += 32) {
+                float xs[32];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) xs[k] = p0 + k < n ? x[p0 + k] : 0.0f;
+                for (int k = 0; k < 32; ++k) xs[k] = p0 + k < b ? x[p0 + k] : 0.0f;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int p = p0 + k;
-                if (p > n) break;
-                if (p == evt) {
-                    while (jl < nb && next_lo == p) {
-                        ms[jl] = P;                          // prefix at the lower bound, replaced by the mean square below
-                        ++jl;
-                        next_lo = jl < nb ? lo_of(jl) : -1;
+                for (int k = 0; k < 32; ++k) {
+                    const int p = p0 + k;
+                    if (p > b) break;
+                    if (p == evt && p < own_hi) {            // (position b belongs to the next slice)
+                        while (jl < nb && next_lo == p) {
+                            plo[jl] = P;
+                            ++jl;
+                            next_lo = jl < nb ? lo_of(jl) : -1;
+                        }
+                        while (jh < nb && next_hi == p) {
+                            phi[jh] = P;
+                            ++jh;
+                            next_hi = jh < nb ? hi_of(jh) : -1;
+                        }
+                        evt = next_event();
                     }
-                    while (jh < nb && next_hi == p) {
-                        const long long lo = lo_of(jh);
-                        ms[jh] = lo < p ? (P - ms[jh]) / (double)(p - lo) : -1.0;   // lib.rs:119 (lo >= hi: skipped)
-                        ++jh;
-                        next_hi = jh < nb ? hi_of(jh) : -1;
+                    if (p < b) {
+                        kw_step(K.cf, (double)xs[k], s1, s2, h1, h2, v);
+                        if (p >= a) P += v * v;
                     }
-                    evt = next_event();
-                }
-                if (p < n) {
-                    kw_step(K.cf, (double)xs[k], s1, s2, h1, h2, v);
-                    P += v * v;
                 }
             }
         }
-        for (long long j = jl > jh ? jh : jl; j < nb; ++j) ms[j] = -1.0;          // bounds at or past the end: lo >= hi
+        // exclusive scan of the slice totals
+        double incl = P;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const double off = incl - P, total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
         if (nb <= 0) {
-            const double m = P / (double)n;
+            const double m = total / (double)n;
             lufs = m <= 0.0 ? NEG_INF : -0.691 + 10.0 * log10(m);
         } else {
+            for (long long j0 = 0; j0 < nb; j0 += 32) {
+                const long long j = j0 + lane;
+                const bool in = j < nb;
+                const long long lo = in ? lo_of(j) : 0, hi = in ? hi_of(j) : 0;
+                const double olo = __shfl_sync(0xffffffffu, off, lane_of(lo));
+                const double ohi = __shfl_sync(0xffffffffu, off, lane_of(hi));
+                if (in) plo[j] = lo < hi ? ((phi[j] + ohi) - (plo[j] + olo)) / (double)(hi - lo) : -1.0;   // lib.rs:119-120
+            }
+            __syncwarp();
             double gate = NEG_INF;
             for (int pass = 0; pass < 2; ++pass) {
                 double sum = 0, cnt = 0;
-                for (long long j = 0; j < nb; ++j) {
-                    const double m = ms[j];
-                    if (m <= 0.0) continue;
+                for (long long j = lane; j < nb; j += 32) {
+                    const double m = plo[j];
+                    if (!(m > 0.0)) continue;
                     const double l = -0.691 + 10.0 * log10(m);
                     const bool keep = pass == 0 ? (l >= -70.0) : (l > gate && l >= -70.0);
                     if (keep) { sum += m; cnt += 1.0; }
                 }
+                sum = warp_sum(sum);
+                cnt = warp_sum(cnt);
                 if (cnt == 0.0) { lufs = NEG_INF; break; }
                 const double mean = sum / cnt;
                 if (pass == 0) gate = -0.691 + 10.0 * log10(mean) - 10.0;
@@ -458,8 +492,10 @@ __global__ void k_kw_serial(KwConfig K, const SectionGeom* __restrict__ geoms, i
             }
         }
     }
-    lufs_out[t] = lufs;
-    gain_out[t] = pow(10.0, (kTargetLufs - lufs) / 20.0);   // lib.rs:221-222
+    if (lane == 0) {
+        lufs_out[t] = lufs;
+        gain_out[t] = pow(10.0, (kTargetLufs - lufs) / 20.0);   // lib.rs:221-222
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -506,6 +542,13 @@ bool kw_config_create(int sample_rate, KwConfig* out, std::string* err)
         K.cell = std::max(1, sample_rate / 10);
         K.k_per_hop = 1;
         K.patch_cells = 1;
+        {
+            // memory of the slowest K-weighting pole (see below): the warm-up of a slice in k_kw_serial
+            const double r = sqrt(fabs(K.cf[11]));
+            int n = 1;
+            while ((double)(n + 1) * (double)(n + 1) * pow(r, (double)n) > 1e-20 && n < 10000000) ++n;
+            K.warm = n + 1;
+        }
         *out = K;
         return true;
     }
@@ -594,7 +637,7 @@ void launch_loudness(const KwConfig& K, const SectionGeom& Gu, const SectionGeom
     if (nsec <= 0) return;
     if (K.general) {
         // energy[] is the per-(chunk, group) block workspace: cells_stride / G slots each
-        k_kw_serial<<<(nsec * G + 31) / 32, 32, 0, st>>>(K, d_geoms, nsec, G, (long long)(cells_stride / G), energy, lufs, gain);
+        k_kw_serial<<<(nsec * G + 3) / 4, 128, 0, st>>>(K, d_geoms, nsec, G, (long long)(cells_stride / G), energy, lufs, gain);
         return;
     }
     static bool attr = false;

@@ -14,6 +14,7 @@ struct KwConfig {
     int k_per_hop;        // cells per hop
     int patch_cells;      // cells after which the filters have forgotten their start state (see k_kw_patch)
     int general;          // 1: 0.1 * rate is not a whole number of samples -> serial path (k_kw_serial)
+    int warm;             // general path: samples after which the filters have forgotten their start state
     const double* mpow;   // device: Mc^1 .. Mc^32 (4x4 row-major each), Mc = state transition over one cell
     const double* imp;    // device: [cell][4] impulse-response states, reversed (same allocation as mpow)
 };
