@@ -1,5 +1,5 @@
 // K2 -- fused spectral multiply + inverse four-step FFT + |.| + per-unit max (or normalised write-out)
-// for the hot shapes M = N1 x 512, N1 in {512, 576, 640}.
+// for the hot shapes M = N1 x 512, N1 in {384, 448, 512, 576, 640} (8 x 8 x R2, R2 = 6 .. 10).
 //
 // Replaces abs(fft_correlation.fft_correlate_1d(section, clip, 'full')), max and the divide of
 // reference audio_pattern_detector.py:491-494 for a whole launch of (chunk x pattern) units.
@@ -10,7 +10,7 @@
 //   k_corr_rows : rows c of  X[c][:] .* H[c][:]  ->  512-point inverse FFT  ->  four-step twiddle  -> W[c][:]
 //   k_corr_cols : columns b of W  ->  N1-point inverse FFT  ->  e^{+i pi m/N}/M  ->  |Re|, |Im|  ->  max / write
 //
-// Both kernels keep one radix-8 (radix-9, radix-10) butterfly per thread in registers, in packed complex
+// Both kernels keep one radix-8 (last column pass: radix-6 .. radix-10) butterfly per thread in registers, in packed complex
 // arithmetic (cpx2.cuh: FADD2/FMUL2/FFMA2), and hand the last pass straight to the epilogue.  All twiddles
 // and all shared-memory addresses are loop invariants of the per-CTA loop over units: the XOR-swizzled
 // exchange layouts (fft_fast.cuh) reduce to "thread constant + immediate" for loads and "thread constant ^
